@@ -1,0 +1,425 @@
+// albvh.cu -- deltas, leaf clustering and bottom-up ALBVH node build.
+//
+// Reference behaviour (GRACE, include/grace/cuda/kernels/albvh.cuh):
+//   compute_deltas_kernel :33-47, build_leaves_kernel :77-234, write_leaves_kernel
+//   :236-295, remove_empty_leaves :826-846, copy_leaf_deltas_kernel :51-74,
+//   build_nodes_slice_kernel/fill_output_queue/fix_node_ranges :303-761 driven by a
+//   host loop with Thrust queue maintenance and a sync per slice (:854-940).
+// The finished arrays are a pure function of (sorted spheres, deltas, max_per_leaf):
+//   parent rule: a subtree [l, r] is the RIGHT child of node l-1 if
+//   delta(l-1) < delta(r), else the LEFT child of node r (ties go right);
+//   leaves = maximal subtrees with <= max_per_leaf primitives.
+//
+// B200 design -- two launches, no host round trip, no Thrust:
+//  (1) leaves_kernel: node j's subtree is [l_j, r_j] with l_j = 1 + (last k < j with
+//      delta_k >= delta_j) and r_j = (first k > j with delta_k > delta_j): the
+//      Cartesian tree of the deltas under the tie rule above.  Each thread bounds its
+//      two scans at max_per_leaf+1 steps over a shared-memory window of deltas, so
+//      "is my left/right child a leaf" needs no atomics and no temporary node array.
+//      Emitted leaves (0..2 per node, ordered by node index == ordered by primitive
+//      range) are compacted in the same kernel with a decoupled look-back scan; the
+//      leaf-level deltas and the zeroed arrival flags are written alongside.
+//  (2) nodes_kernel: classic Karras/Apetrei bottom-up climb over the L leaves with one
+//      global arrival counter per node.  8 lanes cooperate on a leaf's AABB (coalesced
+//      128 B segments of the sphere array), then the group leader climbs, writing its
+//      child index / range end / AABB into the parent's 64-byte record (the reference
+//      layout, cuda/nodes.h:21-36) and continuing only as the second arrival.
+// Algorithmic bytes per particle: deltas 16+4; leaves 4 + (16+4+4)*L/N;
+// nodes 16 + (16 + 2*64)*L/N.
+#include "common.cuh"
+
+#include <math_constants.h>
+
+namespace {
+
+constexpr int LV_THREADS = 256;
+constexpr unsigned long long ST_AGG = 1ull << 62, ST_INCL = 2ull << 62, ST_MASK = 3ull << 62;
+
+// ---------------------------------------------------------------------------
+// deltas
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+deltas_euclid_kernel(const float4* __restrict__ s, size_t n, float* __restrict__ deltas)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t <= n; t += stride) {
+        float d = CUDART_INF_F;
+        if (t >= 1 && t < n) {
+            // generic/functors/albvh.h:78-80 as nvcc contracts it (SASS-verified):
+            // d = dy*dy; d = fma(dx,dx,d); d = fma(dz,dz,d)
+            const float4 a = __ldg(s + t - 1), b = __ldg(s + t);
+            const float dx = __fsub_rn(a.x, b.x), dy = __fsub_rn(a.y, b.y), dz = __fsub_rn(a.z, b.z);
+            d = __fmul_rn(dy, dy);
+            d = __fmaf_rn(dx, dx, d);
+            d = __fmaf_rn(dz, dz, d);
+        }
+        deltas[t] = d;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+deltas_sarea_kernel(const float4* __restrict__ s, size_t n, float* __restrict__ deltas)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t <= n; t += stride) {
+        float d = CUDART_INF_F;
+        if (t >= 1 && t < n) {
+            // generic/functors/albvh.h:101-121: SA = Lx*Lz; fma(Lx,Ly,SA); fma(Ly,Lz,SA)
+            const float4 a = __ldg(s + t - 1), b = __ldg(s + t);
+            const float Lx = __fsub_rn(fmaxf(__fadd_rn(a.x, a.w), __fadd_rn(b.x, b.w)),
+                                       fminf(__fsub_rn(a.x, a.w), __fsub_rn(b.x, b.w)));
+            const float Ly = __fsub_rn(fmaxf(__fadd_rn(a.y, a.w), __fadd_rn(b.y, b.w)),
+                                       fminf(__fsub_rn(a.y, a.w), __fsub_rn(b.y, b.w)));
+            const float Lz = __fsub_rn(fmaxf(__fadd_rn(a.z, a.w), __fadd_rn(b.z, b.w)),
+                                       fminf(__fsub_rn(a.z, a.w), __fsub_rn(b.z, b.w)));
+            d = __fmul_rn(Lx, Lz);
+            d = __fmaf_rn(Lx, Ly, d);
+            d = __fmaf_rn(Ly, Lz, d);
+        }
+        deltas[t] = d;
+    }
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(256)
+deltas_xor_kernel(const KeyT* __restrict__ keys, size_t n, KeyT* __restrict__ deltas)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t <= n; t += stride) {
+        KeyT d = ~KeyT(0);
+        if (t >= 1 && t < n) d = keys[t - 1] ^ keys[t];
+        deltas[t] = d;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// leaves
+// ---------------------------------------------------------------------------
+// d(k) = deltas_shifted[k + 1] is the delta between primitives k and k+1, valid for
+// k in [-1, n-1]; d(-1) and d(n-1) are the sentinels.
+template <typename T, bool STAGED>
+__global__ void __launch_bounds__(LV_THREADS)
+leaves_kernel(const T* __restrict__ deltas_shifted, int n, int mpl,
+              int4* __restrict__ leaves, T* __restrict__ leaf_deltas_shifted,
+              unsigned* __restrict__ node_flags, unsigned long long* __restrict__ block_state,
+              unsigned* __restrict__ ticket, int* __restrict__ n_leaves_out)
+{
+    extern __shared__ __align__(16) unsigned char lv_smem[];
+    T* win = (T*)lv_smem;
+    __shared__ unsigned s_bid;
+    __shared__ unsigned s_warp_tot[LV_THREADS / 32];
+    __shared__ unsigned long long s_excl;
+
+    const int tid = threadIdx.x;
+    if (tid == 0) s_bid = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const unsigned bid = s_bid;
+    const int n_nodes = n - 1;
+    const int j0 = (int)bid * LV_THREADS;
+    const int pad = mpl + 2;
+    // window covers k in [j0 - pad, j0 + LV_THREADS + pad)
+    const int wlo = j0 - pad;
+    if (STAGED) {
+        const int wn = LV_THREADS + 2 * pad;
+        for (int i = tid; i < wn; i += LV_THREADS) {
+            int k = wlo + i;
+            k = max(k, -1);
+            k = min(k, n - 1);
+            win[i] = deltas_shifted[k + 1];
+        }
+        __syncthreads();
+    }
+    auto d = [&](int k) -> T {
+        if (STAGED) return win[k - wlo];
+        return deltas_shifted[k + 1];
+    };
+
+    const int j = j0 + tid;
+    int emit = 0;
+    int l = j, r = j + 1;
+    bool emitL = false, emitR = false;
+    if (j < n_nodes) {
+        const T dj = d(j);
+        while (l > 0 && (j - l + 1) <= mpl && d(l - 1) < dj) --l;
+        while (r < n - 1 && (r - j) <= mpl && !(dj < d(r))) ++r;
+        const int left_size = j - l + 1, right_size = r - j;
+        const bool big = left_size + right_size > mpl;   // sizes are capped at mpl+1
+        emitL = big && left_size <= mpl;
+        emitR = big && right_size <= mpl;
+        emit = (int)emitL + (int)emitR;
+    }
+    // block-wide exclusive scan of emit
+    const int lane = tid & 31, warp = tid >> 5;
+    unsigned incl = emit;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp_tot[warp] = incl;
+    __syncthreads();
+    unsigned add = 0, block_total = 0;
+#pragma unroll
+    for (int w = 0; w < LV_THREADS / 32; ++w) {
+        if (w < warp) add += s_warp_tot[w];
+        block_total += s_warp_tot[w];
+    }
+    const unsigned local_excl = add + incl - emit;
+
+    if (tid == 0) {
+        unsigned long long excl = 0;
+        if (bid == 0) {
+            gb_st_volatile_u64(block_state, (unsigned long long)block_total | ST_INCL);
+        } else {
+            gb_st_volatile_u64(block_state + bid, (unsigned long long)block_total | ST_AGG);
+            int t = (int)bid - 1;
+            for (;;) {
+                const unsigned long long v = gb_ld_volatile_u64(block_state + t);
+                const unsigned long long f = v & ST_MASK;
+                if (f == 0) continue;
+                excl += v & ~ST_MASK;
+                if (f == ST_INCL) break;
+                --t;
+            }
+            gb_st_volatile_u64(block_state + bid, (excl + block_total) | ST_INCL);
+        }
+        s_excl = excl;
+        if ((int)bid == (n_nodes - 1) / LV_THREADS) *n_leaves_out = (int)(excl + block_total);
+        if (bid == 0) leaf_deltas_shifted[0] = deltas_shifted[0];
+    }
+    __syncthreads();
+    if (emit) {
+        unsigned g = (unsigned)s_excl + local_excl;
+        if (emitL) {
+            leaves[g] = make_int4(l, j - l + 1, 0, 0);
+            leaf_deltas_shifted[g + 1] = d(j);          // delta after the leaf's last primitive
+            node_flags[g] = 0u;
+            ++g;
+        }
+        if (emitR) {
+            leaves[g] = make_int4(j + 1, r - j, 0, 0);
+            leaf_deltas_shifted[g + 1] = d(r);
+            node_flags[g] = 0u;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// nodes
+// ---------------------------------------------------------------------------
+constexpr int ND_THREADS = 256;
+constexpr int ND_GROUP = 8;   // lanes cooperating on one leaf's AABB
+
+template <typename T>
+__global__ void __launch_bounds__(ND_THREADS)
+nodes_kernel(const float4* __restrict__ spheres, const int4* __restrict__ leaves,
+             const int* __restrict__ n_leaves_ptr, const T* __restrict__ ld_shifted,
+             int4* nodes, unsigned* flags, int* __restrict__ root)
+{
+    const int L = *n_leaves_ptr;
+    const int n_nodes = L - 1;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane & (ND_GROUP - 1);
+    const int groups_per_block = ND_THREADS / ND_GROUP;
+    const int group = threadIdx.x / ND_GROUP;
+    const int total_groups = gridDim.x * groups_per_block;
+    const int warp_first_group = (threadIdx.x & ~31) / ND_GROUP;
+
+    for (int base = blockIdx.x * groups_per_block + warp_first_group; base < L; base += total_groups) {
+        const int leaf = base + (group - warp_first_group);
+        const bool active = leaf < L;
+        float bx = CUDART_INF_F, by = CUDART_INF_F, bz = CUDART_INF_F;
+        float tx = -CUDART_INF_F, ty = -CUDART_INF_F, tz = -CUDART_INF_F;
+        if (active) {
+            const int4 lf = __ldg(leaves + leaf);
+            for (int i = sub; i < lf.y; i += ND_GROUP) {
+                const float4 s = __ldg(spheres + lf.x + i);
+                // AABBSphere, generic/functors/aabb.h:9-26: centre -/+ h, one FADD each
+                bx = fminf(bx, __fsub_rn(s.x, s.w)); tx = fmaxf(tx, __fadd_rn(s.x, s.w));
+                by = fminf(by, __fsub_rn(s.y, s.w)); ty = fmaxf(ty, __fadd_rn(s.y, s.w));
+                bz = fminf(bz, __fsub_rn(s.z, s.w)); tz = fmaxf(tz, __fadd_rn(s.z, s.w));
+            }
+        }
+#pragma unroll
+        for (int o = 1; o < ND_GROUP; o <<= 1) {
+            bx = fminf(bx, __shfl_xor_sync(0xffffffffu, bx, o));
+            by = fminf(by, __shfl_xor_sync(0xffffffffu, by, o));
+            bz = fminf(bz, __shfl_xor_sync(0xffffffffu, bz, o));
+            tx = fmaxf(tx, __shfl_xor_sync(0xffffffffu, tx, o));
+            ty = fmaxf(ty, __shfl_xor_sync(0xffffffffu, ty, o));
+            tz = fmaxf(tz, __shfl_xor_sync(0xffffffffu, tz, o));
+        }
+        if (!active || sub != 0) continue;
+
+        // ---- climb (group leader only) ----
+        int cur = leaf + n_nodes;      // child index >= n_nodes marks a leaf
+        int l = leaf, r = leaf;
+        for (;;) {
+            const T dl = ld_shifted[l];          // delta(l - 1)
+            const T dr = ld_shifted[r + 1];      // delta(r)
+            const bool right_child = dl < dr;
+            const int parent = right_child ? l - 1 : r;
+            if (parent < 0 || parent >= n_nodes) break;   // cur is the root
+            int* node_i = (int*)(nodes + 4 * (size_t)parent);
+            float* node_f = (float*)node_i;
+            if (right_child) {
+                node_i[1] = cur; node_i[3] = r;
+                *(float4*)(node_f + 8) = make_float4(bx, tx, by, ty);
+                *(float2*)(node_f + 14) = make_float2(bz, tz);
+            } else {
+                node_i[0] = cur; node_i[2] = l;
+                *(float4*)(node_f + 4) = make_float4(bx, tx, by, ty);
+                *(float2*)(node_f + 12) = make_float2(bz, tz);
+            }
+            __threadfence();
+            if (atomicAdd(flags + parent, 1u) == 0u) break;    // first arrival stops
+            __threadfence();
+            const int4 n0 = gb_ld_cg_i4(nodes + 4 * (size_t)parent + 0);
+            const int4 n1 = gb_ld_cg_i4(nodes + 4 * (size_t)parent + 1);
+            const int4 n2 = gb_ld_cg_i4(nodes + 4 * (size_t)parent + 2);
+            const int4 n3 = gb_ld_cg_i4(nodes + 4 * (size_t)parent + 3);
+            cur = parent;
+            l = n0.z; r = n0.w;
+            bx = fminf(__int_as_float(n1.x), __int_as_float(n2.x));
+            tx = fmaxf(__int_as_float(n1.y), __int_as_float(n2.y));
+            by = fminf(__int_as_float(n1.z), __int_as_float(n2.z));
+            ty = fmaxf(__int_as_float(n1.w), __int_as_float(n2.w));
+            bz = fminf(__int_as_float(n3.x), __int_as_float(n3.z));
+            tz = fmaxf(__int_as_float(n3.y), __int_as_float(n3.w));
+            if (r - l == L - 1) *root = cur;
+        }
+    }
+}
+
+int grid_cap(const grace_b200_ctx* ctx, size_t work_items, int per_block, int per_sm)
+{
+    size_t blocks = (work_items + per_block - 1) / per_block;
+    const size_t cap = (size_t)ctx->sm_count * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+template <typename T>
+int build_typed(grace_b200_ctx* ctx, const float4* d_spheres, size_t n, const T* d_deltas,
+                int mpl, int4* d_nodes, int4* d_leaves, int* d_root, cudaStream_t st)
+{
+    const int n_nodes = (int)n - 1;
+    const int lv_blocks = (n_nodes + LV_THREADS - 1) / LV_THREADS;
+    const size_t bytes = gb_align((n + 1) * sizeof(T)) + gb_align(n * sizeof(unsigned)) +
+                         gb_align((size_t)lv_blocks * 8) + 256;
+    void* ws = gb_workspace(ctx, bytes);
+    if (!ws) return GRACE_B200_ENOMEM;
+    GbArena a(ws, bytes);
+    T* leaf_deltas = a.take<T>(n + 1);
+    unsigned* flags = a.take<unsigned>(n);
+    unsigned long long* block_state = a.take<unsigned long long>(lv_blocks);
+    unsigned* ticket = (unsigned*)(ctx->d_scalars + GB_SC_TICKET1);
+    int* d_nleaves = ctx->d_scalars + GB_SC_NLEAVES;
+
+    GB_CUDA(cudaMemsetAsync(block_state, 0, (size_t)lv_blocks * 8, st));
+    GB_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
+    const bool staged = mpl <= 2048;
+    if (staged) {
+        const size_t smem = (size_t)(LV_THREADS + 2 * (mpl + 2)) * sizeof(T);
+        leaves_kernel<T, true><<<lv_blocks, LV_THREADS, smem, st>>>(
+            d_deltas, (int)n, mpl, d_leaves, leaf_deltas, flags, block_state, ticket, d_nleaves);
+    } else {
+        leaves_kernel<T, false><<<lv_blocks, LV_THREADS, 0, st>>>(
+            d_deltas, (int)n, mpl, d_leaves, leaf_deltas, flags, block_state, ticket, d_nleaves);
+    }
+    GB_LAUNCH_CHECK();
+    // Upper bound on leaves is n; expected ~ n / (0.6 * mpl).  Grid-stride over groups.
+    const int nd_blocks = grid_cap(ctx, n / 4 + 1, ND_THREADS / ND_GROUP, 8);
+    nodes_kernel<T><<<nd_blocks, ND_THREADS, 0, st>>>(d_spheres, d_leaves, d_nleaves, leaf_deltas,
+                                                       d_nodes, flags, d_root);
+    GB_LAUNCH_CHECK();
+    return GRACE_B200_OK;
+}
+
+int launch_simple(const grace_b200_ctx* ctx, size_t n) { return grid_cap(ctx, n + 1, 256, 16); }
+
+} // namespace
+
+extern "C" {
+
+int grace_b200_deltas_euclid_f4(grace_b200_ctx* ctx, const float* d_spheres4, size_t n,
+                                float* d_deltas, void* stream)
+{
+    GB_REQUIRE(ctx && d_spheres4 && d_deltas, GRACE_B200_EINVAL, "NULL argument");
+    deltas_euclid_kernel<<<launch_simple(ctx, n), 256, 0, (cudaStream_t)stream>>>(
+        (const float4*)d_spheres4, n, d_deltas);
+    GB_LAUNCH_CHECK();
+    return GRACE_B200_OK;
+}
+
+int grace_b200_deltas_sarea_f4(grace_b200_ctx* ctx, const float* d_spheres4, size_t n,
+                               float* d_deltas, void* stream)
+{
+    GB_REQUIRE(ctx && d_spheres4 && d_deltas, GRACE_B200_EINVAL, "NULL argument");
+    deltas_sarea_kernel<<<launch_simple(ctx, n), 256, 0, (cudaStream_t)stream>>>(
+        (const float4*)d_spheres4, n, d_deltas);
+    GB_LAUNCH_CHECK();
+    return GRACE_B200_OK;
+}
+
+int grace_b200_deltas_xor32(grace_b200_ctx* ctx, const uint32_t* d_keys, size_t n,
+                            uint32_t* d_deltas, void* stream)
+{
+    GB_REQUIRE(ctx && d_keys && d_deltas, GRACE_B200_EINVAL, "NULL argument");
+    deltas_xor_kernel<uint32_t><<<launch_simple(ctx, n), 256, 0, (cudaStream_t)stream>>>(d_keys, n, d_deltas);
+    GB_LAUNCH_CHECK();
+    return GRACE_B200_OK;
+}
+
+int grace_b200_deltas_xor64(grace_b200_ctx* ctx, const uint64_t* d_keys, size_t n,
+                            uint64_t* d_deltas, void* stream)
+{
+    GB_REQUIRE(ctx && d_keys && d_deltas, GRACE_B200_EINVAL, "NULL argument");
+    deltas_xor_kernel<uint64_t><<<launch_simple(ctx, n), 256, 0, (cudaStream_t)stream>>>(d_keys, n, d_deltas);
+    GB_LAUNCH_CHECK();
+    return GRACE_B200_OK;
+}
+
+int grace_b200_albvh_build_f4(grace_b200_ctx* ctx, const float* d_spheres4, size_t n,
+                              const void* d_deltas, int delta_type, int max_per_leaf,
+                              void* d_nodes, void* d_leaves, int* d_root, int* h_n_leaves,
+                              void* stream)
+{
+    GB_REQUIRE(ctx && d_spheres4 && d_deltas && d_nodes && d_leaves && d_root, GRACE_B200_EINVAL,
+               "NULL argument");
+    GB_REQUIRE(max_per_leaf >= 1, GRACE_B200_EINVAL, "max_per_leaf must be >= 1");
+    // albvh.cuh:795-799
+    GB_REQUIRE(n > (size_t)max_per_leaf, GRACE_B200_EINVAL,
+               "max_per_leaf must be less than the total number of primitives.");
+    GB_REQUIRE(n < (1ull << 31) - 1024, GRACE_B200_ERANGE, "more than 2^31 primitives");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if (delta_type == GRACE_B200_DELTA_F32)
+        rc = build_typed<float>(ctx, (const float4*)d_spheres4, n, (const float*)d_deltas,
+                                max_per_leaf, (int4*)d_nodes, (int4*)d_leaves, d_root, st);
+    else if (delta_type == GRACE_B200_DELTA_U32)
+        rc = build_typed<uint32_t>(ctx, (const float4*)d_spheres4, n, (const uint32_t*)d_deltas,
+                                   max_per_leaf, (int4*)d_nodes, (int4*)d_leaves, d_root, st);
+    else if (delta_type == GRACE_B200_DELTA_U64)
+        rc = build_typed<uint64_t>(ctx, (const float4*)d_spheres4, n, (const uint64_t*)d_deltas,
+                                   max_per_leaf, (int4*)d_nodes, (int4*)d_leaves, d_root, st);
+    else
+        return gb_set_error(GRACE_B200_EINVAL, "unknown delta_type %d", delta_type);
+    if (rc) return rc;
+    if (h_n_leaves) return grace_b200_albvh_last_n_leaves(ctx, h_n_leaves, stream);
+    return GRACE_B200_OK;
+}
+
+int grace_b200_albvh_last_n_leaves(grace_b200_ctx* ctx, int* h_n_leaves, void* stream)
+{
+    GB_REQUIRE(ctx && h_n_leaves, GRACE_B200_EINVAL, "NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    GB_CUDA(cudaMemcpyAsync(ctx->h_pinned + GB_SC_NLEAVES, ctx->d_scalars + GB_SC_NLEAVES,
+                            sizeof(int), cudaMemcpyDeviceToHost, st));
+    GB_CUDA(cudaStreamSynchronize(st));
+    *h_n_leaves = ctx->h_pinned[GB_SC_NLEAVES];
+    return GRACE_B200_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,101 @@
+// common.cuh -- shared host/device helpers for the grace_b200 CUDA sources.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "grace_b200.h"
+
+// ---------------------------------------------------------------------------
+// Context: device, SM count, and a grow-only device workspace arena.
+// ---------------------------------------------------------------------------
+struct grace_b200_ctx {
+    int device = 0;
+    int sm_count = 148;
+    char* ws = nullptr;        // workspace arena
+    size_t ws_bytes = 0;
+    int* d_scalars = nullptr;  // small persistent device scalars (tickets, counts)
+    int* h_pinned = nullptr;   // pinned host mirror for count read-backs
+    int last_n_leaves_valid = 0;
+};
+
+// d_scalars layout (ints)
+enum {
+    GB_SC_TICKET0 = 0,      // generic block tickets (self-resetting)
+    GB_SC_TICKET1 = 1,
+    GB_SC_NLEAVES = 2,      // leaf count of the last build
+    GB_SC_TRACE_CTR = 4,    // packet scheduler counter
+    GB_SC_ERRFLAG = 5,      // device-side error flag (trace stack overflow)
+    GB_SC_TOTAL64 = 8,      // 64-bit total (2 ints), 8-byte aligned
+    GB_SC_CLASS = 16,       // segmented sort class counters (8 ints) + XL total (2 ints)
+    GB_SC_COUNT = 64
+};
+
+int gb_set_error(int code, const char* fmt, ...);
+int gb_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+// Returns a pointer to at least `bytes` of workspace (256-byte aligned), growing
+// the arena if needed (growth synchronises the device).  nullptr on failure.
+void* gb_workspace(grace_b200_ctx* ctx, size_t bytes);
+
+#define GB_CUDA(call)                                                         \
+    do {                                                                      \
+        cudaError_t gb_e_ = (call);                                           \
+        if (gb_e_ != cudaSuccess) return gb_cuda_fail(gb_e_, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define GB_LAUNCH_CHECK() GB_CUDA(cudaPeekAtLastError())
+
+#define GB_REQUIRE(cond, code, ...)                                           \
+    do { if (!(cond)) return gb_set_error((code), __VA_ARGS__); } while (0)
+
+static inline size_t gb_align(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// Simple bump allocator over one gb_workspace() block.
+struct GbArena {
+    char* base; size_t off, cap;
+    GbArena(void* p, size_t c) : base((char*)p), off(0), cap(c) {}
+    template <typename T> T* take(size_t count) {
+        size_t bytes = gb_align(count * sizeof(T));
+        T* p = (T*)(base + off);
+        off += bytes;
+        return p;
+    }
+};
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------
+// Device helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned gb_lane() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned gb_lanemask_lt() {
+    unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m;
+}
+
+// Streaming (read-once) 128-bit load / store: keep L1 for data that is reused.
+__device__ __forceinline__ float4 gb_ld_stream_f4(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ unsigned gb_ld_volatile_u32(const unsigned* p) {
+    unsigned v; asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v;
+}
+__device__ __forceinline__ unsigned long long gb_ld_volatile_u64(const unsigned long long* p) {
+    unsigned long long v; asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p)); return v;
+}
+__device__ __forceinline__ void gb_st_volatile_u32(unsigned* p, unsigned v) {
+    asm volatile("st.volatile.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void gb_st_volatile_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+// L2-coherent (L1-bypassing) 128-bit load for data written by other SMs in the same launch.
+__device__ __forceinline__ int4 gb_ld_cg_i4(const int4* p) {
+    int4 r;
+    asm volatile("ld.global.cg.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+#endif

@@ -1,0 +1,98 @@
+// context.cu -- context, workspace arena and error plumbing of the C ABI.
+#include "common.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+static thread_local char g_err[512] = "";
+
+int gb_set_error(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int gb_cuda_fail(cudaError_t e, const char* what, const char* file, int line)
+{
+    return gb_set_error(GRACE_B200_ECUDA, "CUDA error %d (%s) in %s at %s:%d",
+                        (int)e, cudaGetErrorString(e), what, file, line);
+}
+
+void* gb_workspace(grace_b200_ctx* ctx, size_t bytes)
+{
+    if (bytes <= ctx->ws_bytes) return ctx->ws;
+    size_t want = gb_align(bytes + bytes / 8, 1 << 20);
+    // Growth: drain outstanding work that may still use the old arena.
+    if (cudaDeviceSynchronize() != cudaSuccess) return nullptr;
+    if (ctx->ws) cudaFree(ctx->ws);
+    ctx->ws = nullptr;
+    ctx->ws_bytes = 0;
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        gb_set_error(GRACE_B200_ENOMEM, "workspace cudaMalloc(%zu) failed: %s", want,
+                     cudaGetErrorString(e));
+        return nullptr;
+    }
+    ctx->ws = (char*)p;
+    ctx->ws_bytes = want;
+    return p;
+}
+
+extern "C" {
+
+const char* grace_b200_last_error(void) { return g_err; }
+const char* grace_b200_version(void) { return "grace_b200 0.1 (sm_100a)"; }
+
+int grace_b200_create(grace_b200_ctx** out, int device)
+{
+    GB_REQUIRE(out != nullptr, GRACE_B200_EINVAL, "ctx out pointer is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return gb_set_error(GRACE_B200_ECUDA,
+                            "no CUDA device available (%s); grace_b200 has no CPU fallback",
+                            cudaGetErrorString(e));
+    GB_REQUIRE(device >= 0 && device < count, GRACE_B200_EINVAL, "device %d out of range", device);
+    GB_CUDA(cudaSetDevice(device));
+    grace_b200_ctx* ctx = new (std::nothrow) grace_b200_ctx();
+    GB_REQUIRE(ctx != nullptr, GRACE_B200_ENOMEM, "out of host memory");
+    ctx->device = device;
+    cudaDeviceProp prop;
+    GB_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    GB_CUDA(cudaMalloc((void**)&ctx->d_scalars, GB_SC_COUNT * sizeof(int)));
+    GB_CUDA(cudaMemset(ctx->d_scalars, 0, GB_SC_COUNT * sizeof(int)));
+    GB_CUDA(cudaMallocHost((void**)&ctx->h_pinned, GB_SC_COUNT * sizeof(int)));
+    memset(ctx->h_pinned, 0, GB_SC_COUNT * sizeof(int));
+    *out = ctx;
+    return GRACE_B200_OK;
+}
+
+int grace_b200_destroy(grace_b200_ctx* ctx)
+{
+    if (!ctx) return GRACE_B200_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->d_scalars) cudaFree(ctx->d_scalars);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    delete ctx;
+    return GRACE_B200_OK;
+}
+
+int grace_b200_reserve(grace_b200_ctx* ctx, size_t bytes)
+{
+    GB_REQUIRE(ctx != nullptr, GRACE_B200_EINVAL, "ctx is NULL");
+    return gb_workspace(ctx, bytes) ? GRACE_B200_OK : GRACE_B200_ENOMEM;
+}
+
+size_t grace_b200_workspace_bytes(const grace_b200_ctx* ctx) { return ctx ? ctx->ws_bytes : 0; }
+
+} // extern "C"

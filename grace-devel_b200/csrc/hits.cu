@@ -1,0 +1,381 @@
+// hits.cu -- per-ray hit lists: count -> exclusive scan -> fill, and the per-ray
+// stable sort of hits by distance.
+//
+// Reference behaviour (GRACE): trace_sph / trace_with_sentinels_sph,
+// cuda/trace_sph.cuh:112-241 (hit-count pass, two blocking element read-backs,
+// thrust::exclusive_scan, three resizes, fill pass) and sort_by_distance,
+// cuda/sort.cuh:100-131 (new sgpu context per call, thrust::sequence,
+// sgpu::SegSortPairsFromIndices = blocksort + log2(tiles) global merge passes over ALL
+// hits, then two copy+gather passes).
+//
+// B200 design:
+//   * one single-pass decoupled look-back scan turns counts into offsets and a 64-bit
+//     total (one read-back instead of two);
+//   * the segmented sort never merges across segments: ray segments are binned by
+//     length and each is sorted entirely in shared memory by one CTA (bitonic network
+//     on 64-bit (distance bits, position) composites, which makes the result stable by
+//     construction); the permutation is applied to indices and payload in the same
+//     kernel, so each hit is read and written once: 24 B/hit of HBM traffic against
+//     ~12 B x (2 + 2*log2(tiles)) + 32 B for the reference.  Segments longer than the
+//     shared-memory capacity take a global-memory bitonic path.
+#include "common.cuh"
+
+namespace {
+
+constexpr unsigned long long ST_AGG = 1ull << 62, ST_INCL = 2ull << 62, ST_MASK = 3ull << 62;
+constexpr int SC_THREADS = 256, SC_IPT = 8, SC_TILE = SC_THREADS * SC_IPT;
+
+// Exclusive scan of int32 with 64-bit running total.  If add_index != 0, out[i] also
+// gets + i (trace_with_sentinels_sph, trace_sph.cuh:196-207).
+__global__ void __launch_bounds__(SC_THREADS)
+scan_kernel(const int* __restrict__ in, int* __restrict__ out, size_t n, int add_index,
+            unsigned long long* __restrict__ block_state, unsigned* __restrict__ ticket,
+            long long* __restrict__ total_out)
+{
+    __shared__ unsigned s_bid;
+    __shared__ long long s_warp_tot[SC_THREADS / 32];
+    __shared__ long long s_excl;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_bid = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const unsigned bid = s_bid;
+    const size_t base = (size_t)bid * SC_TILE + (size_t)tid * SC_IPT;
+    int v[SC_IPT];
+    long long tsum = 0;
+#pragma unroll
+    for (int i = 0; i < SC_IPT; ++i) {
+        v[i] = (base + i < n) ? in[base + i] : 0;
+        tsum += v[i];
+    }
+    long long incl = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp_tot[warp] = incl;
+    __syncthreads();
+    long long add = 0, block_total = 0;
+#pragma unroll
+    for (int w = 0; w < SC_THREADS / 32; ++w) {
+        if (w < warp) add += s_warp_tot[w];
+        block_total += s_warp_tot[w];
+    }
+    if (tid == 0) {
+        unsigned long long excl = 0;
+        if (bid == 0) {
+            gb_st_volatile_u64(block_state, (unsigned long long)block_total | ST_INCL);
+        } else {
+            gb_st_volatile_u64(block_state + bid, (unsigned long long)block_total | ST_AGG);
+            int t = (int)bid - 1;
+            for (;;) {
+                const unsigned long long s = gb_ld_volatile_u64(block_state + t);
+                const unsigned long long f = s & ST_MASK;
+                if (f == 0) continue;
+                excl += s & ~ST_MASK;
+                if (f == ST_INCL) break;
+                --t;
+            }
+            gb_st_volatile_u64(block_state + bid, (excl + (unsigned long long)block_total) | ST_INCL);
+        }
+        s_excl = (long long)excl;
+        if ((size_t)bid == (n - 1) / SC_TILE && total_out)
+            *total_out = (long long)excl + block_total + (add_index ? (long long)n : 0);
+    }
+    __syncthreads();
+    long long run = s_excl + add + incl - tsum;
+#pragma unroll
+    for (int i = 0; i < SC_IPT; ++i) {
+        if (base + i < n) out[base + i] = (int)(run + (add_index ? (long long)(base + i) : 0));
+        run += v[i];
+    }
+}
+
+int run_scan(grace_b200_ctx* ctx, const int* d_in, int* d_out, size_t n, int add_index,
+             long long* d_total, cudaStream_t st)
+{
+    if (n == 0) {
+        if (d_total) GB_CUDA(cudaMemsetAsync(d_total, 0, sizeof(long long), st));
+        return GRACE_B200_OK;
+    }
+    const size_t blocks = (n + SC_TILE - 1) / SC_TILE;
+    unsigned long long* state = (unsigned long long*)gb_workspace(ctx, blocks * 8 + 256);
+    if (!state) return GRACE_B200_ENOMEM;
+    unsigned* ticket = (unsigned*)(ctx->d_scalars + GB_SC_TICKET1);
+    GB_CUDA(cudaMemsetAsync(state, 0, blocks * 8, st));
+    GB_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
+    scan_kernel<<<(int)blocks, SC_THREADS, 0, st>>>(d_in, d_out, n, add_index, state, ticket, d_total);
+    GB_LAUNCH_CHECK();
+    return GRACE_B200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// segmented sort
+// ---------------------------------------------------------------------------
+// Float distance -> unsigned key with the same ordering as operator< on floats
+// (-0 and +0 compare equal, so both map to the key of +0).
+__device__ __forceinline__ unsigned dist_key(float f)
+{
+    unsigned b = __float_as_uint(f);
+    if ((b << 1) == 0u) b = 0u;
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+constexpr int N_CLASSES = 5;
+// class capacities (elements); class 4 = anything larger (global path)
+__host__ __device__ constexpr int class_cap(int c)
+{
+    return c == 0 ? 32 : c == 1 ? 512 : c == 2 ? 2048 : c == 3 ? 8192 : 0x7fffffff;
+}
+
+// Bin segments by length.  lists: [N_CLASSES][n_rays] ray ids; counts: [N_CLASSES];
+// xl_total: total elements in class-4 segments (padded to pow2 per segment).
+__global__ void __launch_bounds__(256)
+classify_kernel(const int* __restrict__ offsets, int n_rays, long long total,
+                int* __restrict__ lists, int* __restrict__ counts,
+                unsigned long long* __restrict__ xl_total, unsigned long long* __restrict__ xl_offsets)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rays) return;
+    const long long b = offsets[r];
+    const long long e = (r + 1 < n_rays) ? (long long)offsets[r + 1] : total;
+    const long long len = e - b;
+    if (len <= 1) return;
+    int c = 0;
+    while (len > class_cap(c)) ++c;
+    const int slot = atomicAdd(counts + c, 1);
+    lists[(size_t)c * n_rays + slot] = r;
+    if (c == N_CLASSES - 1) {
+        unsigned long long m = 1;
+        while ((long long)m < len) m <<= 1;
+        xl_offsets[slot] = atomicAdd(xl_total, m);
+    }
+}
+
+template <int CAP, int NT>
+__global__ void __launch_bounds__(NT)
+segsort_smem_kernel(float* __restrict__ dist, const int* __restrict__ offsets, int n_rays,
+                    long long total, int* __restrict__ idx, unsigned* __restrict__ data,
+                    const int* __restrict__ list, const int* __restrict__ count_ptr)
+{
+    extern __shared__ __align__(16) unsigned char ss_smem[];
+    unsigned long long* comp = (unsigned long long*)ss_smem;
+    const int n_seg = *count_ptr;
+    constexpr int PER = (CAP + NT - 1) / NT;
+    for (int s = blockIdx.x; s < n_seg; s += gridDim.x) {
+        const int r = list[s];
+        const long long b = offsets[r];
+        const long long e = (r + 1 < n_rays) ? (long long)offsets[r + 1] : total;
+        const int len = (int)(e - b);
+        int m = 1;
+        while (m < len) m <<= 1;
+        for (int i = threadIdx.x; i < m; i += NT)
+            comp[i] = i < len ? ((unsigned long long)dist_key(dist[b + i]) << 32) | (unsigned)i
+                              : ~0ull;
+        __syncthreads();
+        for (int k = 2; k <= m; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = threadIdx.x; t < (m >> 1); t += NT) {
+                    // index of the lower element of the t-th compare-exchange pair
+                    const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const int hi = lo | j;
+                    const bool up = (lo & k) == 0;
+                    const unsigned long long a = comp[lo], c = comp[hi];
+                    if ((a > c) == up) { comp[lo] = c; comp[hi] = a; }
+                }
+                __syncthreads();
+            }
+        }
+        // apply the permutation: read everything first, then write (in place)
+        float dv[PER]; int iv[PER]; unsigned pv[PER];
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const int i = threadIdx.x + q * NT;
+            if (i < len) {
+                const unsigned src = (unsigned)(comp[i] & 0xffffffffu);
+                dv[q] = dist[b + src]; iv[q] = idx[b + src]; pv[q] = data[b + src];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const int i = threadIdx.x + q * NT;
+            if (i < len) { dist[b + i] = dv[q]; idx[b + i] = iv[q]; data[b + i] = pv[q]; }
+        }
+        __syncthreads();
+    }
+}
+
+// Global-memory path for segments above the shared-memory capacity: one CTA per
+// segment, bitonic network on a padded power-of-two scratch range.
+__global__ void __launch_bounds__(1024)
+segsort_global_kernel(float* __restrict__ dist, const int* __restrict__ offsets, int n_rays,
+                      long long total, int* __restrict__ idx, unsigned* __restrict__ data,
+                      const int* __restrict__ list, const int* __restrict__ count_ptr,
+                      const unsigned long long* __restrict__ xl_offsets,
+                      unsigned long long* __restrict__ comp_all, float* __restrict__ tmp_d,
+                      int* __restrict__ tmp_i, unsigned* __restrict__ tmp_p)
+{
+    const int n_seg = *count_ptr;
+    const int NT = blockDim.x;
+    for (int s = blockIdx.x; s < n_seg; s += gridDim.x) {
+        const int r = list[s];
+        const long long b = offsets[r];
+        const long long e = (r + 1 < n_rays) ? (long long)offsets[r + 1] : total;
+        const long long len = e - b;
+        long long m = 1;
+        while (m < len) m <<= 1;
+        unsigned long long* comp = comp_all + xl_offsets[s];
+        for (long long i = threadIdx.x; i < m; i += NT)
+            comp[i] = i < len ? ((unsigned long long)dist_key(dist[b + i]) << 32) | (unsigned)i
+                              : ~0ull;
+        __syncthreads();
+        for (long long k = 2; k <= m; k <<= 1) {
+            for (long long j = k >> 1; j > 0; j >>= 1) {
+                for (long long t = threadIdx.x; t < (m >> 1); t += NT) {
+                    const long long lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const long long hi = lo | j;
+                    const bool up = (lo & k) == 0;
+                    const unsigned long long a = comp[lo], c = comp[hi];
+                    if ((a > c) == up) { comp[lo] = c; comp[hi] = a; }
+                }
+                __syncthreads();
+            }
+        }
+        float* td = tmp_d + xl_offsets[s]; int* ti = tmp_i + xl_offsets[s]; unsigned* tp = tmp_p + xl_offsets[s];
+        for (long long i = threadIdx.x; i < len; i += NT) {
+            const unsigned src = (unsigned)(comp[i] & 0xffffffffu);
+            td[i] = dist[b + src]; ti[i] = idx[b + src]; tp[i] = data[b + src];
+        }
+        __syncthreads();
+        for (long long i = threadIdx.x; i < len; i += NT) {
+            dist[b + i] = td[i]; idx[b + i] = ti[i]; data[b + i] = tp[i];
+        }
+        __syncthreads();
+    }
+}
+
+template <int CAP, int NT>
+int launch_smem_class(grace_b200_ctx* ctx, int cls, float* dist, const int* offsets, int n_rays,
+                      long long total, int* idx, unsigned* data, const int* lists, const int* counts,
+                      int h_count, cudaStream_t st)
+{
+    if (h_count == 0) return GRACE_B200_OK;
+    const size_t smem = (size_t)CAP * 8;
+    GB_CUDA(cudaFuncSetAttribute(segsort_smem_kernel<CAP, NT>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, segsort_smem_kernel<CAP, NT>, NT, smem));
+    if (per_sm < 1) per_sm = 1;
+    int blocks = ctx->sm_count * per_sm;
+    if (blocks > h_count) blocks = h_count;
+    segsort_smem_kernel<CAP, NT><<<blocks, NT, smem, st>>>(
+        dist, offsets, n_rays, total, idx, data, lists + (size_t)cls * n_rays, counts + cls);
+    GB_LAUNCH_CHECK();
+    return GRACE_B200_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int grace_b200_exclusive_scan_i32(grace_b200_ctx* ctx, const int* d_in, int* d_out, size_t n,
+                                  long long* d_total, void* stream)
+{
+    GB_REQUIRE(ctx && (n == 0 || (d_in && d_out)), GRACE_B200_EINVAL, "NULL argument");
+    return run_scan(ctx, d_in, d_out, n, 0, d_total, (cudaStream_t)stream);
+}
+
+int grace_b200_trace_hits_count_f4(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, size_t n_rays,
+                                   const float* d_spheres4, size_t n, const grace_b200_tree* tree,
+                                   int with_sentinels, int* d_ray_offsets, long long* h_total_hits,
+                                   void* stream)
+{
+    GB_REQUIRE(ctx && d_ray_offsets && h_total_hits, GRACE_B200_EINVAL, "NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = grace_b200_trace_hitcounts_f4(ctx, d_rays, n_rays, d_spheres4, n, tree, d_ray_offsets, stream);
+    if (rc) return rc;
+    long long* d_total = (long long*)(ctx->d_scalars + GB_SC_TOTAL64);
+    rc = run_scan(ctx, d_ray_offsets, d_ray_offsets, n_rays, with_sentinels ? 1 : 0, d_total, st);
+    if (rc) return rc;
+    long long* h_total = (long long*)(ctx->h_pinned + GB_SC_TOTAL64);
+    GB_CUDA(cudaMemcpyAsync(h_total, d_total, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    GB_CUDA(cudaStreamSynchronize(st));
+    *h_total_hits = *h_total;
+    // trace_sph.cuh:117,137: offsets and totals are int in the reference
+    GB_REQUIRE(*h_total_hits <= 0x7fffffffLL, GRACE_B200_ERANGE,
+               "%lld hits exceed the 32-bit offsets of the reference layout; tile the rays",
+               *h_total_hits);
+    return GRACE_B200_OK;
+}
+
+int grace_b200_sort_by_distance(grace_b200_ctx* ctx, float* d_hit_distances, const int* d_ray_offsets,
+                                size_t n_rays, size_t total_hits, int* d_hit_indices,
+                                void* d_hit_data, void* stream)
+{
+    GB_REQUIRE(ctx && d_ray_offsets, GRACE_B200_EINVAL, "NULL argument");
+    GB_REQUIRE(n_rays < (1ull << 31) && total_hits < (1ull << 31), GRACE_B200_ERANGE, "too many rays/hits");
+    if (n_rays == 0 || total_hits == 0) return GRACE_B200_OK;
+    GB_REQUIRE(d_hit_distances && d_hit_indices && d_hit_data, GRACE_B200_EINVAL, "NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nr = (int)n_rays;
+    const size_t list_bytes = gb_align((size_t)N_CLASSES * n_rays * sizeof(int));
+    const size_t xl_off_bytes = gb_align(n_rays * 8);
+    char* ws = (char*)gb_workspace(ctx, list_bytes + xl_off_bytes + 256);
+    if (!ws) return GRACE_B200_ENOMEM;
+    int* lists = (int*)ws;
+    unsigned long long* xl_offsets = (unsigned long long*)(ws + list_bytes);
+    int* counts = ctx->d_scalars + GB_SC_CLASS;                       // 8 ints
+    unsigned long long* xl_total = (unsigned long long*)(ctx->d_scalars + GB_SC_CLASS + 8);
+    GB_CUDA(cudaMemsetAsync(counts, 0, 10 * sizeof(int), st));
+    classify_kernel<<<(nr + 255) / 256, 256, 0, st>>>(d_ray_offsets, nr, (long long)total_hits, lists,
+                                                      counts, xl_total, xl_offsets);
+    GB_LAUNCH_CHECK();
+    int* h = ctx->h_pinned + GB_SC_CLASS;
+    GB_CUDA(cudaMemcpyAsync(h, counts, 10 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    GB_CUDA(cudaStreamSynchronize(st));
+    float* dist = d_hit_distances;
+    int* idx = d_hit_indices;
+    unsigned* data = (unsigned*)d_hit_data;
+    const long long total = (long long)total_hits;
+    int rc;
+    if ((rc = launch_smem_class<32, 32>(ctx, 0, dist, d_ray_offsets, nr, total, idx, data, lists, counts, h[0], st))) return rc;
+    if ((rc = launch_smem_class<512, 128>(ctx, 1, dist, d_ray_offsets, nr, total, idx, data, lists, counts, h[1], st))) return rc;
+    if ((rc = launch_smem_class<2048, 256>(ctx, 2, dist, d_ray_offsets, nr, total, idx, data, lists, counts, h[2], st))) return rc;
+    if ((rc = launch_smem_class<8192, 1024>(ctx, 3, dist, d_ray_offsets, nr, total, idx, data, lists, counts, h[3], st))) return rc;
+    if (h[4] > 0) {
+        const unsigned long long xl = *(unsigned long long*)(h + 8);
+        // the workspace is still holding lists/xl_offsets: extend it without moving them
+        const size_t head = list_bytes + xl_off_bytes + 256;
+        const size_t need = head + gb_align(xl * 8) + 3 * gb_align(xl * 4) + 256;
+        if (need > ctx->ws_bytes) {
+            // grow: copy lists through a fresh allocation (rare path)
+            void* keep = nullptr;
+            GB_CUDA(cudaMalloc(&keep, head));
+            GB_CUDA(cudaMemcpyAsync(keep, ws, head, cudaMemcpyDeviceToDevice, st));
+            GB_CUDA(cudaStreamSynchronize(st));
+            char* nws = (char*)gb_workspace(ctx, need);
+            if (!nws) { cudaFree(keep); return GRACE_B200_ENOMEM; }
+            GB_CUDA(cudaMemcpyAsync(nws, keep, head, cudaMemcpyDeviceToDevice, st));
+            GB_CUDA(cudaStreamSynchronize(st));
+            cudaFree(keep);
+            ws = nws;
+            lists = (int*)ws;
+            xl_offsets = (unsigned long long*)(ws + list_bytes);
+        }
+        char* p = ws + head;
+        unsigned long long* comp = (unsigned long long*)p; p += gb_align(xl * 8);
+        float* td = (float*)p; p += gb_align(xl * 4);
+        int* ti = (int*)p; p += gb_align(xl * 4);
+        unsigned* tp = (unsigned*)p;
+        int blocks = ctx->sm_count * 2;
+        if (blocks > h[4]) blocks = h[4];
+        segsort_global_kernel<<<blocks, 1024, 0, st>>>(dist, d_ray_offsets, nr, total, idx, data,
+                                                       lists + (size_t)4 * n_rays, counts + 4,
+                                                       xl_offsets, comp, td, ti, tp);
+        GB_LAUNCH_CHECK();
+    }
+    return GRACE_B200_OK;
+}
+
+} // extern "C"

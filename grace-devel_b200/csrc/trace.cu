@@ -1,0 +1,317 @@
+// trace.cu -- packet traversal of the ALBVH with SPH kernel line integrals.
+//
+// Reference behaviour (GRACE): gpu::trace_kernel, cuda/kernels/bintree_trace.cuh:52-197
+// (warp = packet of 32 consecutive rays sharing one stack; a child is pushed when ANY
+// lane hits its box, right first then left; at a leaf every lane tests every
+// primitive), AABBs_hit cuda/device/intersect.cuh:10-40 with the integer 3-input
+// min/max of cuda/device/intrinsics.cuh:8-52, sphere_hit generic/intersect.h:10-55,
+// functors cuda/functors/trace.cuh:163-235, entry points cuda/trace_sph.cuh:58-241.
+// The reference caps the grid at 112 blocks x 8 warps (kernel_config.h:11), fetches a
+// node with four dependent texture reads and re-uploads the LUT on every call.
+//
+// B200 design:
+//   * one warp per packet, packets handed out by an atomic ticket to a persistent
+//     grid sized to fill all 148 SMs (dynamic load balance: packet costs vary by
+//     orders of magnitude on clustered SPH data);
+//   * traversal stack is warp-uniform: top of stack in a register, the rest in a
+//     per-warp shared-memory array;
+//   * the 64-byte node is fetched with four 128-bit read-only loads issued together;
+//   * leaf primitives are staged once per packet into shared memory (coalesced
+//     128-bit loads) and broadcast from there;
+//   * the 51-entry double-precision kernel table lives in shared memory for the whole
+//     launch and in constant memory between launches (no per-call upload);
+//   * every floating-point expression that decides a hit, or feeds the integral, is
+//     written with explicit round-to-nearest intrinsics in the contraction pattern
+//     nvcc gives the reference (DESIGN.md "numeric contract"), so hit sets are
+//     bit-identical to the reference's CUDA build.
+#include "common.cuh"
+
+#include <math_constants.h>
+
+namespace {
+
+constexpr int TR_THREADS = 128;          // 4 packets per CTA
+constexpr int TR_WARPS = TR_THREADS / 32;
+constexpr int TR_STACK = 96;             // reference STACK_SIZE is 64 (kernel_config.h:13)
+constexpr int N_TABLE = 51;
+
+enum { MODE_COUNT = 0, MODE_CUMULATIVE = 1, MODE_FILL = 2 };
+
+// Numeric data of cuda/trace_sph.cuh:32-48: line integrals of the Gadget-2 cubic
+// spline at impact parameter b/h = i/50.
+__constant__ double c_kernel_table[N_TABLE] = {
+    1.90986019771937, 1.90563449910964, 1.89304415940934, 1.87230928086763,
+    1.84374947679902, 1.80776276033034, 1.76481079856299, 1.71540816859939,
+    1.66011373131439, 1.59952322363667, 1.53426266082279, 1.46498233888091,
+    1.39235130929287, 1.31705223652377, 1.23977618317103, 1.16121278415369,
+    1.08201943664419, 1.00288866679720, 0.924475767210246, 0.847415371038733,
+    0.772316688105931, 0.699736940377312, 0.630211918937167, 0.564194562399538,
+    0.502076205853037, 0.444144023534733, 0.390518196140658, 0.341148855945766,
+    0.295941946237307, 0.254782896476983, 0.217538645099225, 0.184059547649710,
+    0.154181189781890, 0.127726122453554, 0.104505535066266,
+    8.432088120445191E-002, 6.696547102921641E-002, 5.222604427168923E-002,
+    3.988433820097490E-002, 2.971866601747601E-002, 2.150552303075515E-002,
+    1.502124104014533E-002, 1.004371608622562E-002, 6.354242122978656E-003,
+    3.739494884706115E-003, 1.993729589156428E-003, 9.212900163813992E-004,
+    3.395908945333921E-004, 8.287326418242995E-005, 7.387919939044624E-006,
+    0.000000000000000E+000
+};
+const double h_kernel_table[N_TABLE] = {
+    1.90986019771937, 1.90563449910964, 1.89304415940934, 1.87230928086763,
+    1.84374947679902, 1.80776276033034, 1.76481079856299, 1.71540816859939,
+    1.66011373131439, 1.59952322363667, 1.53426266082279, 1.46498233888091,
+    1.39235130929287, 1.31705223652377, 1.23977618317103, 1.16121278415369,
+    1.08201943664419, 1.00288866679720, 0.924475767210246, 0.847415371038733,
+    0.772316688105931, 0.699736940377312, 0.630211918937167, 0.564194562399538,
+    0.502076205853037, 0.444144023534733, 0.390518196140658, 0.341148855945766,
+    0.295941946237307, 0.254782896476983, 0.217538645099225, 0.184059547649710,
+    0.154181189781890, 0.127726122453554, 0.104505535066266,
+    8.432088120445191E-002, 6.696547102921641E-002, 5.222604427168923E-002,
+    3.988433820097490E-002, 2.971866601747601E-002, 2.150552303075515E-002,
+    1.502124104014533E-002, 1.004371608622562E-002, 6.354242122978656E-003,
+    3.739494884706115E-003, 1.993729589156428E-003, 9.212900163813992E-004,
+    3.395908945333921E-004, 8.287326418242995E-005, 7.387919939044624E-006,
+    0.000000000000000E+000
+};
+
+// Two-box slab test, bit-for-bit AABBs_hit (cuda/device/intersect.cuh:16-39):
+// t = (plane - o) * invd (FADD then FMUL), per-axis FMNMX, then the three-input
+// min/max stages as SIGNED INTEGER compares on the float bit patterns, final >=.
+__device__ __forceinline__ bool slab_hit(float bx, float tx, float by, float ty, float bz, float tz,
+                                         float ox, float oy, float oz,
+                                         float ix, float iy, float iz, float len)
+{
+    const float tbx = __fmul_rn(__fsub_rn(bx, ox), ix);
+    const float ttx = __fmul_rn(__fsub_rn(tx, ox), ix);
+    const float tby = __fmul_rn(__fsub_rn(by, oy), iy);
+    const float tty = __fmul_rn(__fsub_rn(ty, oy), iy);
+    const float tbz = __fmul_rn(__fsub_rn(bz, oz), iz);
+    const float ttz = __fmul_rn(__fsub_rn(tz, oz), iz);
+    const int zmin = max(min(__float_as_int(tbz), __float_as_int(ttz)), 0);
+    const int zmax = min(max(__float_as_int(tbz), __float_as_int(ttz)), __float_as_int(len));
+    const int tmin = max(max(__float_as_int(fminf(tbx, ttx)), __float_as_int(fminf(tby, tty))), zmin);
+    const int tmax = min(min(__float_as_int(fmaxf(tbx, ttx)), __float_as_int(fmaxf(tby, tty))), zmax);
+    return __int_as_float(tmax) >= __int_as_float(tmin);
+}
+
+// generic/intersect.h:16-48 in the SASS-verified contraction:
+//   dot = fma(pz,rz, fma(px,rx, py*ry)); b_k = fma(-r_k, dot, p_k);
+//   b2 = fma(bz,bz, fma(bx,bx, by*by)); hit iff !(b2 >= h*h) && !(dot < 0) && !(dot >= len)
+__device__ __forceinline__ bool sphere_test(const float4 s, float ox, float oy, float oz,
+                                            float dx, float dy, float dz, float len,
+                                            float& b2, float& dot)
+{
+    const float px = __fsub_rn(s.x, ox), py = __fsub_rn(s.y, oy), pz = __fsub_rn(s.z, oz);
+    dot = __fmul_rn(py, dy);
+    dot = __fmaf_rn(px, dx, dot);
+    dot = __fmaf_rn(pz, dz, dot);
+    const float bx = __fmaf_rn(-dx, dot, px);
+    const float by = __fmaf_rn(-dy, dot, py);
+    const float bz = __fmaf_rn(-dz, dot, pz);
+    b2 = __fmul_rn(by, by);
+    b2 = __fmaf_rn(bx, bx, b2);
+    b2 = __fmaf_rn(bz, bz, b2);
+    const float r2 = __fmul_rn(s.w, s.w);
+    return !(b2 >= r2) && !(dot < 0.0f) && !(dot >= len);
+}
+
+// cuda/functors/trace.cuh:183-186 + generic/interpolate.h:15-38 (device branch).
+__device__ __forceinline__ float kernel_integral(float b2, float h, const double* table)
+{
+    const float ir = __fdiv_rn(1.0f, h);
+    float x = __fmul_rn(__fmul_rn(__fsqrt_rn(b2), ir), 50.0f);
+    int i = __float2int_rz(x);
+    if (i >= N_TABLE - 1) { x = (float)(N_TABLE - 1); i = N_TABLE - 2; }
+    i = max(i, 0);
+    const double y0 = table[i], y1 = table[i + 1];
+    const double t = __dsub_rn((double)x, (double)i);
+    const double y = __fma_rn(t, __dsub_rn(y1, y0), y0);
+    return __fmul_rn((float)y, __fmul_rn(ir, ir));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(TR_THREADS)
+trace_kernel(const grace_b200_ray* __restrict__ rays, int n_packets,
+             const float4* __restrict__ spheres,
+             const int4* __restrict__ nodes, const int4* __restrict__ leaves,
+             int n_nodes, const int* __restrict__ root_ptr, int max_per_leaf,
+             int* __restrict__ out_counts, float* __restrict__ out_cum,
+             const int* __restrict__ offsets, int* __restrict__ hit_idx,
+             float* __restrict__ hit_integral, float* __restrict__ hit_dist,
+             int* __restrict__ packet_counter, int* __restrict__ err_flag)
+{
+    extern __shared__ __align__(16) unsigned char tr_smem[];
+    // layout: [double table 51 (+pad)] [stacks TR_WARPS x TR_STACK int] [prims TR_WARPS x mpl float4]
+    double* s_table = (double*)tr_smem;
+    int* s_stack_all = (int*)(tr_smem + 52 * sizeof(double));
+    float4* s_prims_all = (float4*)(s_stack_all + TR_WARPS * TR_STACK);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (MODE != MODE_COUNT) {
+        for (int i = threadIdx.x; i < N_TABLE; i += TR_THREADS) s_table[i] = c_kernel_table[i];
+        __syncthreads();
+    }
+    int* stack = s_stack_all + warp * TR_STACK;
+    float4* s_prims = s_prims_all + warp * max_per_leaf;
+    const int root = __ldg(root_ptr);
+
+    for (;;) {
+        int packet = 0;
+        if (lane == 0) packet = atomicAdd(packet_counter, 1);
+        packet = __shfl_sync(0xffffffffu, packet, 0);
+        if (packet >= n_packets) break;
+        const int ray_index = packet * 32 + lane;
+
+        const grace_b200_ray ray = rays[ray_index];
+        const float ix = __fdiv_rn(1.0f, ray.dx), iy = __fdiv_rn(1.0f, ray.dy),
+                    iz = __fdiv_rn(1.0f, ray.dz);
+        int count = 0;
+        float cum = 0.0f;
+        int cursor = 0;
+        if (MODE == MODE_FILL) cursor = offsets[ray_index];
+
+        int sp = 0;            // number of entries below the register top
+        int top = root;        // top of stack lives in a register; -1 = empty
+        while (top >= 0) {
+            if (top < n_nodes) {
+                const int4* np = nodes + 4 * (size_t)top;
+                const int4 n0 = __ldg(np + 0);
+                const int4 n1 = __ldg(np + 1);
+                const int4 n2 = __ldg(np + 2);
+                const int4 n3 = __ldg(np + 3);
+                const bool hitL = slab_hit(__int_as_float(n1.x), __int_as_float(n1.y),
+                                           __int_as_float(n1.z), __int_as_float(n1.w),
+                                           __int_as_float(n3.x), __int_as_float(n3.y),
+                                           ray.ox, ray.oy, ray.oz, ix, iy, iz, ray.length);
+                const bool hitR = slab_hit(__int_as_float(n2.x), __int_as_float(n2.y),
+                                           __int_as_float(n2.z), __int_as_float(n2.w),
+                                           __int_as_float(n3.z), __int_as_float(n3.w),
+                                           ray.ox, ray.oy, ray.oz, ix, iy, iz, ray.length);
+                const bool anyL = __any_sync(0xffffffffu, hitL);
+                const bool anyR = __any_sync(0xffffffffu, hitR);
+                // pop, then push right, then left: left ends up on top
+                if (anyL && anyR) {
+                    if (sp >= TR_STACK) { if (lane == 0) *err_flag = 1; top = -1; sp = 0; continue; }
+                    stack[sp++] = n0.y;
+                    top = n0.x;
+                } else if (anyL) {
+                    top = n0.x;
+                } else if (anyR) {
+                    top = n0.y;
+                } else {
+                    top = sp > 0 ? stack[--sp] : -1;
+                }
+            } else {
+                const int4 leaf = __ldg(leaves + (top - n_nodes));
+                top = sp > 0 ? stack[--sp] : -1;
+                for (int i = lane; i < leaf.y; i += 32) s_prims[i] = __ldg(spheres + leaf.x + i);
+                __syncwarp();
+                for (int i = 0; i < leaf.y; ++i) {
+                    const float4 s = s_prims[i];
+                    float b2, dot;
+                    if (sphere_test(s, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, ray.length,
+                                    b2, dot)) {
+                        if (MODE == MODE_COUNT) {
+                            ++count;
+                        } else if (MODE == MODE_CUMULATIVE) {
+                            cum = __fadd_rn(cum, kernel_integral(b2, s.w, s_table));
+                        } else {
+                            hit_idx[cursor] = leaf.x + i;
+                            hit_integral[cursor] = kernel_integral(b2, s.w, s_table);
+                            hit_dist[cursor] = dot;
+                            ++cursor;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        if (MODE == MODE_COUNT) out_counts[ray_index] = count;
+        if (MODE == MODE_CUMULATIVE) out_cum[ray_index] = cum;
+    }
+}
+
+size_t trace_smem_bytes(int max_per_leaf)
+{
+    return 52 * sizeof(double) + (size_t)TR_WARPS * TR_STACK * sizeof(int) +
+           (size_t)TR_WARPS * max_per_leaf * sizeof(float4);
+}
+
+template <int MODE>
+int launch_trace(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, size_t n_rays,
+                 const float* d_spheres4, size_t n, const grace_b200_tree* tree,
+                 int* out_counts, float* out_cum, const int* offsets, int* hit_idx,
+                 float* hit_integral, float* hit_dist, cudaStream_t st)
+{
+    GB_REQUIRE(ctx && d_rays && d_spheres4 && tree && tree->d_nodes && tree->d_leaves && tree->d_root,
+               GRACE_B200_EINVAL, "NULL argument");
+    // bintree_trace.cuh:231-238
+    GB_REQUIRE(n_rays % 32 == 0, GRACE_B200_EINVAL,
+               "Number of rays must be a multiple of the warp size (32).");
+    GB_REQUIRE(n_rays < (1ull << 31), GRACE_B200_ERANGE, "more than 2^31 rays in one call");
+    GB_REQUIRE(tree->n_leaves >= 2 && tree->max_per_leaf >= 1, GRACE_B200_EINVAL, "malformed tree");
+    (void)n;
+    if (n_rays == 0) return GRACE_B200_OK;
+    const int n_packets = (int)(n_rays / 32);
+    const size_t smem = trace_smem_bytes(tree->max_per_leaf);
+    GB_REQUIRE(smem <= 200 * 1024, GRACE_B200_EINVAL, "max_per_leaf too large for shared memory staging");
+    GB_CUDA(cudaFuncSetAttribute(trace_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel<MODE>, TR_THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    int blocks = ctx->sm_count * per_sm;
+    const int need = (n_packets + TR_WARPS - 1) / TR_WARPS;
+    if (blocks > need) blocks = need;
+    int* counter = ctx->d_scalars + GB_SC_TRACE_CTR;
+    GB_CUDA(cudaMemsetAsync(counter, 0, 2 * sizeof(int), st));   // counter + error flag
+    trace_kernel<MODE><<<blocks, TR_THREADS, smem, st>>>(
+        d_rays, n_packets, (const float4*)d_spheres4, (const int4*)tree->d_nodes,
+        (const int4*)tree->d_leaves, tree->n_leaves - 1, tree->d_root, tree->max_per_leaf,
+        out_counts, out_cum, offsets, hit_idx, hit_integral, hit_dist, counter,
+        ctx->d_scalars + GB_SC_ERRFLAG);
+    GB_LAUNCH_CHECK();
+    return GRACE_B200_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const double* grace_b200_kernel_integral_table(int* n_table)
+{
+    if (n_table) *n_table = N_TABLE;
+    return h_kernel_table;
+}
+
+int grace_b200_trace_hitcounts_f4(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, size_t n_rays,
+                                  const float* d_spheres4, size_t n, const grace_b200_tree* tree,
+                                  int* d_hit_counts, void* stream)
+{
+    GB_REQUIRE(d_hit_counts, GRACE_B200_EINVAL, "NULL output");
+    return launch_trace<MODE_COUNT>(ctx, d_rays, n_rays, d_spheres4, n, tree, d_hit_counts, nullptr,
+                                    nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int grace_b200_trace_cumulative_f4(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, size_t n_rays,
+                                   const float* d_spheres4, size_t n, const grace_b200_tree* tree,
+                                   float* d_cumulated, void* stream)
+{
+    GB_REQUIRE(d_cumulated, GRACE_B200_EINVAL, "NULL output");
+    return launch_trace<MODE_CUMULATIVE>(ctx, d_rays, n_rays, d_spheres4, n, tree, nullptr,
+                                         d_cumulated, nullptr, nullptr, nullptr, nullptr,
+                                         (cudaStream_t)stream);
+}
+
+int grace_b200_trace_hits_fill_f4(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, size_t n_rays,
+                                  const float* d_spheres4, size_t n, const grace_b200_tree* tree,
+                                  const int* d_ray_offsets, int* d_hit_indices,
+                                  float* d_hit_integrals, float* d_hit_distances, void* stream)
+{
+    GB_REQUIRE(d_ray_offsets && d_hit_indices && d_hit_integrals && d_hit_distances,
+               GRACE_B200_EINVAL, "NULL argument");
+    return launch_trace<MODE_FILL>(ctx, d_rays, n_rays, d_spheres4, n, tree, nullptr, nullptr,
+                                   d_ray_offsets, d_hit_indices, d_hit_integrals, d_hit_distances,
+                                   (cudaStream_t)stream);
+}
+
+} // extern "C"

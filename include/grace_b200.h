@@ -1,0 +1,252 @@
+/*
+ * grace_b200.h -- C ABI of the B200-native GRACE ray-tracing hot path.
+ *
+ * GRACE (spthm/grace-devel) has no C ABI: its boundary is a set of header
+ * templates in namespace grace that user .cu files call directly.  Each entry
+ * point below replaces one of those templates for the SPH (float4 sphere) path;
+ * the citation after "replaces:" is the reference interface (paths relative to
+ * the GRACE tree).  include/grace/ *.h in this repo re-creates the reference's
+ * C++ names on top of this ABI.
+ *
+ * Conventions
+ *   - every pointer named d_* is DEVICE memory owned by the caller; h_* is host
+ *     memory; sizes are element counts;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*; NULL is
+ *     the legacy default stream).  Calls that must return a count to the host
+ *     (documented per function) synchronise that stream, the others do not;
+ *   - temporaries come from the context's workspace arena, which only grows;
+ *     a context must not be used from two host threads at once (the reference
+ *     is not re-entrant either: cuda/kernels/bintree_trace.cuh:37-38);
+ *   - return value: 0 = success, otherwise a GRACE_B200_E* code;
+ *     grace_b200_last_error() gives the message of the calling thread's last
+ *     failure.  The C++ shim maps GRACE_B200_EINVAL to std::invalid_argument and
+ *     CUDA failures to print+exit, as the reference does (error.h:35-64,
+ *     bintree_trace.cuh:231-238, albvh.cuh:795-799).
+ *   - there is no CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef GRACE_B200_H
+#define GRACE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define GRACE_B200_OK       0
+#define GRACE_B200_EINVAL   1   /* bad argument (reference: std::invalid_argument) */
+#define GRACE_B200_ECUDA    2   /* CUDA runtime failure */
+#define GRACE_B200_ERANGE   3   /* size exceeds what the 32-bit reference layout can hold */
+#define GRACE_B200_ENOMEM   4
+
+/* Delta (key-difference) element types accepted by the tree builder. */
+#define GRACE_B200_DELTA_F32 0
+#define GRACE_B200_DELTA_U32 1
+#define GRACE_B200_DELTA_U64 2
+
+/* grace::RaySortType, include/grace/types.h:47-51 */
+#define GRACE_B200_NO_SORT        0
+#define GRACE_B200_DIRECTION_SORT 1
+#define GRACE_B200_ENDPOINT_SORT  2
+
+typedef struct grace_b200_ctx grace_b200_ctx;
+
+/* grace::Ray, include/grace/ray.h:5-10 (7 floats, 28 bytes, direction normalised). */
+typedef struct { float dx, dy, dz, ox, oy, oz, length; } grace_b200_ray;
+
+/* ---- context ---------------------------------------------------------------- */
+int grace_b200_create(grace_b200_ctx** ctx, int device);
+int grace_b200_destroy(grace_b200_ctx* ctx);
+const char* grace_b200_last_error(void);
+const char* grace_b200_version(void);
+/* Pre-size the workspace arena (optional; avoids growth inside timed regions). */
+int grace_b200_reserve(grace_b200_ctx* ctx, size_t bytes);
+size_t grace_b200_workspace_bytes(const grace_b200_ctx* ctx);
+
+/* ---- bounds + Morton keys --------------------------------------------------- */
+/* replaces: AABB::compute_centroids + min_vec3/max_vec3
+ *   (cuda/kernels/aabb.cuh:14-49, cuda/util/extrema.cuh:502-513,667-678) as used by
+ *   morton_keys(prims, keys, centroid, bots, tops) (cuda/kernels/morton.cuh:139-173).
+ * d_bounds6 receives {min x,y,z, max x,y,z} of the sphere centres (device). */
+int grace_b200_bounds_f4(grace_b200_ctx* ctx, const float* d_spheres4, size_t n,
+                         float* d_bounds6, void* stream);
+/* Component-wise min and max of all four components {x,y,z,w} (min_vec4/max_vec4,
+ * min_max_x: cuda/util/extrema.cuh:189-230,456-731).  d_minmax8 = {min xyzw, max xyzw}. */
+int grace_b200_minmax_f4(grace_b200_ctx* ctx, const float* d_spheres4, size_t n,
+                         float* d_minmax8, void* stream);
+
+/* replaces: morton_keys_sph / morton::morton_keys_kernel
+ *   (cuda/build_sph.cuh:19-34, cuda/kernels/morton.cuh:30-55,97-116).
+ * key = interleave(trunc(scale*(c - bot))), scale = span/(top-bot), 10 or 21 bits
+ * per axis.  Bounds are read from device memory so no host sync is needed. */
+int grace_b200_morton_keys30_f4(grace_b200_ctx* ctx, const float* d_spheres4, size_t n,
+                                const float* d_bounds6, uint32_t* d_keys, void* stream);
+int grace_b200_morton_keys63_f4(grace_b200_ctx* ctx, const float* d_spheres4, size_t n,
+                                const float* d_bounds6, uint64_t* d_keys, void* stream);
+
+/* ---- stable key-value radix sort -------------------------------------------- */
+/* replaces: thrust::sort_by_key(keys, values) (cuda/build_sph.cuh:46,57,70,81;
+ *   cuda/kernels/gen_rays.cuh:483,520,577,615).  Stable LSD onesweep sort on key
+ * bits [0, key_bits).  Keys and values are sorted in place; value_bytes is the
+ * record size (16 = float4 sphere, 28 = Ray, 4 = plain 32-bit payload).
+ * d_perm (optional, may be NULL) receives the permutation sorted[i] = in[perm[i]]. */
+int grace_b200_sort_pairs_u32(grace_b200_ctx* ctx, uint32_t* d_keys, void* d_values,
+                              int value_bytes, size_t n, int key_bits,
+                              uint32_t* d_perm, void* stream);
+int grace_b200_sort_pairs_u64(grace_b200_ctx* ctx, uint64_t* d_keys, void* d_values,
+                              int value_bytes, size_t n, int key_bits,
+                              uint32_t* d_perm, void* stream);
+
+/* replaces: morton_keys30_sort_sph / morton_keys63_sort_sph (cuda/build_sph.cuh:41-82).
+ * key_bits = 30 or 63.  h_bot3/h_top3 = explicit bounds, or both NULL to compute
+ * them from the centres.  d_keys_out (optional) receives the sorted keys
+ * (uint32_t[n] or uint64_t[n]).  Spheres are sorted in place. */
+int grace_b200_morton_sort_f4(grace_b200_ctx* ctx, float* d_spheres4, size_t n, int key_bits,
+                              const float* h_bot3, const float* h_top3,
+                              void* d_keys_out, void* stream);
+
+/* ---- deltas ----------------------------------------------------------------- */
+/* replaces: compute_deltas + DeltaEuclidean / DeltaSurfaceArea / DeltaXOR
+ *   (cuda/kernels/albvh.cuh:33-47,950-978; generic/functors/albvh.h:17-126;
+ *    cuda/build_sph.cuh:87-114).  Outputs n+1 deltas, shifted by one, with
+ *   +inf / all-ones sentinels at both ends. */
+int grace_b200_deltas_euclid_f4(grace_b200_ctx* ctx, const float* d_spheres4, size_t n,
+                                float* d_deltas, void* stream);
+int grace_b200_deltas_sarea_f4(grace_b200_ctx* ctx, const float* d_spheres4, size_t n,
+                               float* d_deltas, void* stream);
+int grace_b200_deltas_xor32(grace_b200_ctx* ctx, const uint32_t* d_keys, size_t n,
+                            uint32_t* d_deltas, void* stream);
+int grace_b200_deltas_xor64(grace_b200_ctx* ctx, const uint64_t* d_keys, size_t n,
+                            uint64_t* d_deltas, void* stream);
+
+/* ---- ALBVH build ------------------------------------------------------------ */
+/* replaces: build_ALBVH / ALBVH_sph (cuda/kernels/albvh.cuh:986-1072,
+ *   cuda/build_sph.cuh:118-124) = build_leaves + remove_empty_leaves +
+ *   copy_leaf_deltas + build_nodes.
+ * d_nodes  : int4[4*(n-1)] capacity; on return the first 4*(L-1) hold the
+ *            reference layout (cuda/nodes.h:21-36);
+ * d_leaves : int4[n] capacity; first L valid, {first, count, 0, 0};
+ * d_root   : device int, index of the root node (Tree::root_index_ptr);
+ * h_n_leaves: host int receiving L; when non-NULL the stream is synchronised.
+ *            When NULL nothing is synchronised and L can be read later with
+ *            grace_b200_albvh_last_n_leaves().
+ * Returns GRACE_B200_EINVAL if n <= max_per_leaf (albvh.cuh:795-799). */
+int grace_b200_albvh_build_f4(grace_b200_ctx* ctx, const float* d_spheres4, size_t n,
+                              const void* d_deltas, int delta_type, int max_per_leaf,
+                              void* d_nodes, void* d_leaves, int* d_root,
+                              int* h_n_leaves, void* stream);
+int grace_b200_albvh_last_n_leaves(grace_b200_ctx* ctx, int* h_n_leaves, void* stream);
+
+/* ---- trace ------------------------------------------------------------------ */
+/* A tree as the trace entry points take it (grace::Tree, cuda/nodes.h:14-58). */
+typedef struct {
+    const void* d_nodes;    /* int4[4*(n_leaves-1)] */
+    const void* d_leaves;   /* int4[n_leaves]       */
+    const int*  d_root;     /* device int           */
+    int n_leaves;
+    int max_per_leaf;
+} grace_b200_tree;
+
+/* All trace calls return GRACE_B200_EINVAL unless n_rays % 32 == 0
+ * (bintree_trace.cuh:231-238): a packet is 32 consecutive rays. */
+
+/* replaces: trace_hitcounts_sph (cuda/trace_sph.cuh:58-79). */
+int grace_b200_trace_hitcounts_f4(grace_b200_ctx* ctx, const grace_b200_ray* d_rays,
+                                  size_t n_rays, const float* d_spheres4, size_t n,
+                                  const grace_b200_tree* tree, int* d_hit_counts, void* stream);
+/* replaces: trace_cumulative_sph (cuda/trace_sph.cuh:82-109). */
+int grace_b200_trace_cumulative_f4(grace_b200_ctx* ctx, const grace_b200_ray* d_rays,
+                                   size_t n_rays, const float* d_spheres4, size_t n,
+                                   const grace_b200_tree* tree, float* d_cumulated, void* stream);
+/* replaces: trace_sph / trace_with_sentinels_sph (cuda/trace_sph.cuh:112-241), split in
+ * two calls because a C ABI cannot resize the caller's vectors:
+ *   _count : pass 1 (hit counts) + exclusive scan -> d_ray_offsets[n_rays];
+ *            *h_total_hits = sum of counts (stream is synchronised).  With
+ *            with_sentinels != 0 each offset is shifted by its ray index and the
+ *            total includes one sentinel slot per ray (trace_sph.cuh:196-207).
+ *   _fill  : pass 2 writes (sphere index, kernel integral, distance) per hit in
+ *            emission order starting at d_ray_offsets[ray].
+ * Returns GRACE_B200_ERANGE if the total exceeds INT32_MAX (the reference's
+ * offsets are int, trace_sph.cuh:117,137): tile the rays. */
+int grace_b200_trace_hits_count_f4(grace_b200_ctx* ctx, const grace_b200_ray* d_rays,
+                                   size_t n_rays, const float* d_spheres4, size_t n,
+                                   const grace_b200_tree* tree, int with_sentinels,
+                                   int* d_ray_offsets, long long* h_total_hits, void* stream);
+int grace_b200_trace_hits_fill_f4(grace_b200_ctx* ctx, const grace_b200_ray* d_rays,
+                                  size_t n_rays, const float* d_spheres4, size_t n,
+                                  const grace_b200_tree* tree, const int* d_ray_offsets,
+                                  int* d_hit_indices, float* d_hit_integrals,
+                                  float* d_hit_distances, void* stream);
+
+/* replaces: sort_by_distance (cuda/sort.cuh:100-131 -> sgpu::SegSortPairsFromIndices,
+ *   external/sgpu/kernels/segmentedsort.cuh:732-779, + two order_by_index gathers).
+ * Stable ascending sort of each ray's segment [offsets[r], offsets[r+1]) by distance;
+ * indices and the 32-bit payload d_hit_data are permuted identically, in place. */
+int grace_b200_sort_by_distance(grace_b200_ctx* ctx, float* d_hit_distances,
+                                const int* d_ray_offsets, size_t n_rays, size_t total_hits,
+                                int* d_hit_indices, void* d_hit_data, void* stream);
+
+/* The 51-entry kernel line-integral table (cuda/trace_sph.cuh:22-50). */
+const double* grace_b200_kernel_integral_table(int* n_table);
+
+/* ---- ray generators --------------------------------------------------------- */
+/* replaces: uniform_random_rays / uniform_random_rays_single_octant
+ *   (cuda/gen_rays.cuh:26-96 -> cuda/kernels/gen_rays.cuh:104-205,416-522):
+ *   cuRAND XORWOW normals, double rnorm3d normalisation, 30-bit direction Morton
+ *   key, stable sort by key.  octant < 0 = full sphere, else grace::Octants 0..7. */
+int grace_b200_uniform_random_rays(grace_b200_ctx* ctx, grace_b200_ray* d_rays, size_t n_rays,
+                                   float ox, float oy, float oz, float length,
+                                   int octant, unsigned long long seed, void* stream);
+/* replaces: one_to_many_rays (cuda/gen_rays.cuh:98-186 -> kernels/gen_rays.cuh:209-244,526-617).
+ * d_points: n_rays records of point_stride_floats floats, xyz first.  For
+ * GRACE_B200_ENDPOINT_SORT h_bot3/h_top3 give the key bounds (NULL -> computed). */
+int grace_b200_one_to_many_rays(grace_b200_ctx* ctx, grace_b200_ray* d_rays, size_t n_rays,
+                                float ox, float oy, float oz, const float* d_points,
+                                int point_stride_floats, int sort_type,
+                                const float* h_bot3, const float* h_top3, void* stream);
+/* replaces: plane_parallel_random_rays (cuda/gen_rays.cuh:188-238 -> kernels :247-316,620-664). */
+int grace_b200_plane_parallel_random_rays(grace_b200_ctx* ctx, grace_b200_ray* d_rays,
+                                          int width, int height, const float* h_base3,
+                                          const float* h_w3, const float* h_h3, float length,
+                                          unsigned long long seed, void* stream);
+/* replaces: orthographic_projection_rays (cuda/gen_rays.cuh:240-290 -> kernels :319-360,667-725). */
+int grace_b200_orthographic_projection_rays(grace_b200_ctx* ctx, grace_b200_ray* d_rays,
+                                            int resolution_x, int resolution_y,
+                                            const float* h_camera_position3,
+                                            const float* h_look_at3, const float* h_view_up3,
+                                            float vertical_extent, float length, void* stream);
+/* replaces: pinhole_camera_rays (cuda/gen_rays.cuh:292-399 -> kernels :362-395,727-787). */
+int grace_b200_pinhole_camera_rays(grace_b200_ctx* ctx, grace_b200_ray* d_rays,
+                                   int resolution_x, int resolution_y,
+                                   const float* h_camera_position3, const float* h_look_at3,
+                                   const float* h_view_up3, float fov_y, float length,
+                                   void* stream);
+/* HEALPix NESTED pixel centres as one-to-many rays from (ox,oy,oz): directions
+ * pix2vec_nest(nside, first_pixel + i) (RayVectorGeneration/src/chealpix/chealpix.c:
+ * 112-126,357-391,459-467), all of the given length. */
+int grace_b200_healpix_rays(grace_b200_ctx* ctx, grace_b200_ray* d_rays, size_t n_rays,
+                            long nside, long first_pixel, float ox, float oy, float oz,
+                            float length, void* stream);
+
+/* ---- utilities used by the drivers ------------------------------------------ */
+/* Synthetic Gadget-shaped SPH snapshot: float4 {x,y,z,h} in [0,1)^3,
+ * 30 % uniform background + 70 % in Plummer halos, h from the analytic local
+ * density with N_ngb = 32, stored in Peano-Hilbert cell order (2^7 cells/side). */
+int grace_b200_synth_gadget_f4(grace_b200_ctx* ctx, float* d_spheres4, size_t n,
+                               unsigned int seed, void* stream);
+/* Exclusive prefix sum of int32 (thrust::exclusive_scan, trace_sph.cuh:135);
+ * d_total (device, 64-bit, may be NULL) receives the grand total. */
+int grace_b200_exclusive_scan_i32(grace_b200_ctx* ctx, const int* d_in, int* d_out, size_t n,
+                                  long long* d_total, void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRACE_B200_H */

@@ -1,0 +1,316 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the ctypes mirror of the
+reference's API) against the CPU oracle on the same seeded inputs.
+Bit-exact for keys, order, tree arrays, hit counts and hit lists; column densities
+are also required bit-exact here (both sum hits in ascending primitive order),
+with 1e-5 relative as the documented contract."""
+import numpy as np
+import pytest
+import torch
+
+from util import uniform_spheres, clustered_spheres, isotropic_rays, ortho_rays_z
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def as_u(t):
+    a = host(t)
+    return a.view(np.uint32) if a.dtype == np.int32 else a.view(np.uint64)
+
+
+def build_both(gb, orc, s, mpl, bits=30, bot=None, top=None, delta="euclid"):
+    """Sort + deltas + tree on the GPU and in the oracle from the same input."""
+    d_s = dev(s)
+    fn = gb.morton_keys30_sort_sph if bits == 30 else gb.morton_keys63_sort_sph
+    d_keys = fn(d_s, bot, top, return_keys=True)
+    hs, hk, perm = orc.sort_spheres(s, bits, bot, top)
+    n = len(s)
+    if delta == "euclid":
+        d_d = torch.empty(n + 1, dtype=torch.float32, device="cuda")
+        gb.euclidean_deltas_sph(d_s, d_d)
+        hd = orc.deltas_euclid(hs)
+    elif delta == "sarea":
+        d_d = torch.empty(n + 1, dtype=torch.float32, device="cuda")
+        gb.surface_area_deltas_sph(d_s, d_d)
+        hd = orc.deltas_sarea(hs)
+    else:
+        d_d = torch.empty(n + 1, dtype=d_keys.dtype, device="cuda")
+        gb.XOR_deltas_sph(d_keys, d_d)
+        hd = orc.deltas_xor(hk)
+    tree = gb.Tree(n, mpl)
+    gb.ALBVH_sph(d_s, d_d, tree)
+    htree = orc.build_tree(hs, hd, mpl)
+    return d_s, d_keys, d_d, tree, hs, hk, hd, htree
+
+
+def assert_tree_equal(tree, htree):
+    assert tree.n_leaves == htree.n_leaves
+    assert np.array_equal(host(tree.leaves)[:, :2], htree.leaves[:, :2])
+    assert int(tree.root_index_ptr.item()) == htree.root
+    assert np.array_equal(host(tree.nodes), htree.nodes)
+
+
+# ----------------------------------------------------------------------------- keys
+def test_bounds_and_minmax(gb, orc):
+    s = clustered_spheres(100003, seed=1)
+    d_s = dev(s)
+    lo, hi = orc.bounds(s)
+    assert np.array_equal(host(gb.min_vec3(d_s)), lo)
+    assert np.array_equal(host(gb.max_vec3(d_s)), hi)
+    assert np.array_equal(host(gb.max_vec4(d_s)), s.max(0))
+    assert gb.min_max_x(d_s) == (float(s[:, 0].min()), float(s[:, 0].max()))
+
+
+@pytest.mark.parametrize("bits", [30, 63])
+@pytest.mark.parametrize("explicit", [True, False])
+def test_morton_keys(gb, orc, bits, explicit):
+    s = uniform_spheres(77777, seed=2) * np.float32(2.0) - np.float32(1.0)  # [-1, 1)
+    d_s = dev(s)
+    keys = torch.empty(len(s), dtype=torch.int32 if bits == 30 else torch.int64, device="cuda")
+    if explicit:
+        bot, top = np.full(3, -1, np.float32), np.full(3, 1, np.float32)
+        gb.morton_keys_sph(d_s, keys, bot, top)
+    else:
+        bot, top = orc.bounds(s)
+        gb.morton_keys_sph(d_s, keys)
+    assert np.array_equal(as_u(keys), orc.morton_keys(s, bot, top, bits))
+
+
+def test_morton_keys_out_of_range_and_nan(gb, orc):
+    # cvt.rzi saturation / NaN -> 0 (F2I.TRUNC semantics of the reference kernel)
+    s = np.array([[-5, 0.5, 2.0, 1], [np.nan, 1.0, 0.999, 1], [0.25, np.inf, -np.inf, 1],
+                  [1e30, -1e30, 0.5, 1]], np.float32)
+    s = np.tile(s, (40, 1))
+    bot, top = np.zeros(3, np.float32), np.ones(3, np.float32)
+    for bits, dt in ((30, torch.int32), (63, torch.int64)):
+        keys = torch.empty(len(s), dtype=dt, device="cuda")
+        gb.morton_keys_sph(dev(s), keys, bot, top)
+        assert np.array_equal(as_u(keys), orc.morton_keys(s, bot, top, bits))
+
+
+# ----------------------------------------------------------------------------- sort
+@pytest.mark.parametrize("n", [1, 31, 6144, 6145, 200001])
+@pytest.mark.parametrize("kbits", [32, 64])
+def test_sort_pairs_stable(gb, orc, n, kbits):
+    rng = np.random.default_rng(n + kbits)
+    if kbits == 32:
+        keys = rng.integers(0, 1 << 12, n).astype(np.uint32) * np.uint32(262147)  # many duplicates
+        d_k = dev(keys.view(np.int32))
+    else:
+        keys = rng.integers(0, 1 << 16, n).astype(np.uint64) * np.uint64(281474976710677)
+        d_k = dev(keys.view(np.int64))
+    vals = rng.random((n, 4), dtype=np.float32)
+    d_v = dev(vals)
+    perm = gb.sort_by_key(d_k, d_v, return_perm=True)
+    ref = orc.sort_perm(keys)
+    assert np.array_equal(host(perm), ref)
+    assert np.array_equal(as_u(d_k), keys[ref])
+    assert np.array_equal(host(d_v), vals[ref])
+
+
+def test_sort_ray_payload_and_key_bits(gb, orc):
+    rng = np.random.default_rng(5)
+    n = 50021
+    keys = rng.integers(0, 1 << 30, n).astype(np.uint32)
+    rays = rng.random((n, 7), dtype=np.float32)
+    d_k, d_r = dev(keys.view(np.int32)), dev(rays)
+    gb.sort_by_key(d_k, d_r, key_bits=30)
+    ref = orc.sort_perm(keys)
+    assert np.array_equal(host(d_r), rays[ref])
+    vals = np.arange(n, dtype=np.int32)
+    d_k, d_v = dev(keys.view(np.int32)), dev(vals)
+    gb.sort_by_key(d_k, d_v)
+    assert np.array_equal(host(d_v), ref)
+
+
+@pytest.mark.parametrize("bits", [30, 63])
+def test_morton_sort_spheres(gb, orc, bits):
+    s = clustered_spheres(150000, seed=7)       # clustered => many duplicate 30-bit keys
+    d_s = dev(s)
+    fn = gb.morton_keys30_sort_sph if bits == 30 else gb.morton_keys63_sort_sph
+    keys = fn(d_s, return_keys=True)
+    hs, hk, perm = orc.sort_spheres(s, bits)
+    assert np.array_equal(as_u(keys), hk)
+    assert np.array_equal(host(d_s), hs)
+
+
+# ----------------------------------------------------------------------------- deltas + tree
+def test_deltas(gb, orc):
+    s = clustered_spheres(60000, seed=8)
+    hs, hk, _ = orc.sort_spheres(s, 30)
+    d_s = dev(hs)
+    d = torch.empty(len(s) + 1, dtype=torch.float32, device="cuda")
+    gb.euclidean_deltas_sph(d_s, d)
+    assert np.array_equal(host(d).view(np.uint32), orc.deltas_euclid(hs).view(np.uint32))
+    gb.surface_area_deltas_sph(d_s, d)
+    assert np.array_equal(host(d).view(np.uint32), orc.deltas_sarea(hs).view(np.uint32))
+    for bits, dt in ((30, torch.int32), (63, torch.int64)):
+        hk = orc.morton_keys(hs, *orc.bounds(hs), bits)
+        dk = dev(hk.view(np.int32 if bits == 30 else np.int64))
+        dd = torch.empty(len(s) + 1, dtype=dt, device="cuda")
+        gb.XOR_deltas_sph(dk, dd)
+        assert np.array_equal(as_u(dd), orc.deltas_xor(hk))
+
+
+@pytest.mark.parametrize("mpl", [1, 2, 8, 32, 100])
+@pytest.mark.parametrize("data", ["uniform", "clustered"])
+def test_tree_bit_exact(gb, orc, mpl, data):
+    n = 120000
+    s = uniform_spheres(n, seed=mpl) if data == "uniform" else clustered_spheres(n, seed=mpl)
+    out = build_both(gb, orc, s, mpl)
+    assert_tree_equal(out[3], out[7])
+
+
+@pytest.mark.parametrize("delta,bits", [("xor", 30), ("xor", 63), ("sarea", 30)])
+def test_tree_other_deltas(gb, orc, delta, bits):
+    s = clustered_spheres(90000, seed=21)
+    out = build_both(gb, orc, s, 16, bits=bits, delta=delta)
+    assert_tree_equal(out[3], out[7])
+
+
+def test_tree_tiny_and_errors(gb, orc):
+    s = np.array([[-0.5, -0.5, -0.5, 0.2], [0.5, 0.5, 0.5, 0.2]], np.float32)
+    out = build_both(gb, orc, s, 1, bot=-np.ones(3, np.float32), top=np.ones(3, np.float32))
+    assert_tree_equal(out[3], out[7])
+    with pytest.raises(ValueError):           # albvh.cuh:795-799
+        d = torch.empty(3, dtype=torch.float32, device="cuda")
+        gb.ALBVH_sph(dev(s), d, gb.Tree(2, 2))
+    s3 = uniform_spheres(33, seed=1)
+    out = build_both(gb, orc, s3, 32)
+    assert_tree_equal(out[3], out[7])
+
+
+# ----------------------------------------------------------------------------- trace
+@pytest.fixture(scope="module")
+def scene(gb, orc):
+    s = clustered_spheres(1 << 17, seed=3)
+    d_s, _, _, tree, hs, _, _, htree = build_both(gb, orc, s, 32)
+    rays = isotropic_rays(1 << 12, origin=(0.5, 0.5, 0.5), length=2.0, seed=4)
+    return d_s, tree, hs, htree, rays
+
+
+def test_hitcounts_exact(gb, orc, scene):
+    d_s, tree, hs, htree, rays = scene
+    out = torch.empty(len(rays), dtype=torch.int32, device="cuda")
+    gb.trace_hitcounts_sph(dev(rays), d_s, tree, out)
+    ref = orc.trace_hitcounts(rays, hs, htree)
+    assert np.array_equal(host(out), ref)
+    sub = slice(0, 256)
+    assert np.array_equal(host(out)[sub], orc.brute_hitcounts(rays[sub], hs))
+
+
+def test_hitcounts_config1(gb, orc):
+    # BASELINE config 1: 2^16 uniform spheres (radii < 0.1), 2^14 isotropic rays from the
+    # box centre, length 2, explicit bounds (0,0,0)-(1,1,1); checked against brute force.
+    s = uniform_spheres(1 << 16, seed=1234)
+    bot, top = np.zeros(3, np.float32), np.ones(3, np.float32)
+    d_s, _, _, tree, hs, _, _, htree = build_both(gb, orc, s, 32, bot=bot, top=top)
+    rays = isotropic_rays(1 << 14, seed=1234)
+    out = torch.empty(len(rays), dtype=torch.int32, device="cuda")
+    gb.trace_hitcounts_sph(dev(rays), d_s, tree, out)
+    assert np.array_equal(host(out), orc.brute_hitcounts(rays, hs))
+
+
+def test_cumulative(gb, orc, scene):
+    d_s, tree, hs, htree, rays = scene
+    out = torch.empty(len(rays), dtype=torch.float32, device="cuda")
+    gb.trace_cumulative_sph(dev(rays), d_s, tree, out)
+    ref = orc.trace_cumulative(rays, hs, htree)
+    got = host(out)
+    rel = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-30)
+    assert rel.max() <= 1e-5          # the contract (north_star)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))   # and in fact bit-exact
+
+
+def test_hit_lists_and_sort(gb, orc, scene):
+    d_s, tree, hs, htree, rays = scene
+    rays = rays[:1024]
+    off = torch.empty(len(rays), dtype=torch.int32, device="cuda")
+    idx, integ, dist = gb.trace_sph(dev(rays), d_s, tree, off)
+    roff, ridx, rinteg, rdist = orc.trace_hits(rays, hs, htree)
+    assert np.array_equal(host(off), roff)
+    assert np.array_equal(host(idx), ridx)
+    assert np.array_equal(host(dist).view(np.uint32), rdist.view(np.uint32))
+    assert np.array_equal(host(integ).view(np.uint32), rinteg.view(np.uint32))
+    gb.sort_by_distance(dist, off, idx, integ)
+    sd, si, sg = orc.sort_by_distance(rdist, roff, ridx, rinteg)
+    assert np.array_equal(host(dist).view(np.uint32), sd.view(np.uint32))
+    assert np.array_equal(host(idx), si)
+    assert np.array_equal(host(integ).view(np.uint32), sg.view(np.uint32))
+
+
+def test_hit_lists_with_sentinels(gb, orc, scene):
+    d_s, tree, hs, htree, rays = scene
+    rays = rays[:256]
+    off = torch.empty(len(rays), dtype=torch.int32, device="cuda")
+    idx, integ, dist = gb.trace_with_sentinels_sph(dev(rays), d_s, tree, off, -7, -1.0, 1e30)
+    roff, ridx, rinteg, rdist = orc.trace_hits(rays, hs, htree)
+    counts = np.diff(np.append(roff, len(ridx)))
+    assert np.array_equal(host(off), roff + np.arange(len(rays)))
+    assert len(idx) == len(ridx) + len(rays)
+    hi = host(idx)
+    for r in (0, 17, 255):
+        b = roff[r] + r
+        assert np.array_equal(hi[b:b + counts[r]], ridx[roff[r]:roff[r] + counts[r]])
+        assert hi[b + counts[r]] == -7 and host(dist)[b + counts[r]] == np.float32(1e30)
+
+
+def test_segsort_all_classes(gb, orc):
+    # segment lengths straddling every size class incl. the global-memory path
+    lens = [0, 1, 2, 31, 32, 33, 500, 512, 513, 2048, 2049, 8192, 8193, 20000, 3, 0, 40000]
+    rng = np.random.default_rng(3)
+    total = sum(lens)
+    dist = rng.integers(0, 1000, total).astype(np.float32) / np.float32(7.0)   # many ties
+    dist[5] = 0.0
+    dist[6] = -0.0
+    idx = rng.integers(0, 1 << 30, total).astype(np.int32)
+    data = rng.random(total, dtype=np.float32)
+    off = np.concatenate([[0], np.cumsum(lens[:-1])]).astype(np.int32)
+    d_dist, d_idx, d_data, d_off = dev(dist), dev(idx), dev(data), dev(off)
+    gb.sort_by_distance(d_dist, d_off, d_idx, d_data)
+    sd, si, sg = orc.sort_by_distance(dist, off, idx, data)
+    assert np.array_equal(host(d_dist), sd)
+    assert np.array_equal(host(d_idx), si)
+    assert np.array_equal(host(d_data), sg)
+
+
+def test_exclusive_scan(gb):
+    rng = np.random.default_rng(0)
+    for n in (1, 2047, 2048, 2049, 1000003):
+        a = rng.integers(0, 5000, n).astype(np.int32)
+        out, total = gb.exclusive_scan(dev(a))
+        ref = np.concatenate([[0], np.cumsum(a[:-1], dtype=np.int64)])
+        assert np.array_equal(host(out).astype(np.int64), ref)
+        assert int(total.item()) == int(a.sum(dtype=np.int64))
+
+
+def test_two_sphere_volume_integral(gb):
+    # tests/integrate/integrate.cu:48-101 through the CUDA path
+    radius = 0.2
+    s = np.array([[-0.5, -0.5, -0.5, radius], [0.5, 0.5, 0.5, radius]], np.float32)
+    d_s = dev(s)
+    tree = gb.Tree(2, 1)
+    gb.build_tree(d_s, tree, -np.ones(3, np.float32), np.ones(3, np.float32))
+    n_side = 512
+    span = 2.0 + 2 * radius
+    rays = ortho_rays_z(n_side, -1.0 - radius, 1.0 + radius)
+    rays[:, 5] = 1.0 + radius
+    rays[:, 6] = 2 * span
+    out = torch.empty(len(rays), dtype=torch.float32, device="cuda")
+    gb.trace_cumulative_sph(dev(rays), d_s, tree, out)
+    total = float(out.double().sum()) * (span / n_side) ** 2 / 2
+    assert abs(1.0 - total) < 5e-4
+
+
+def test_rays_not_multiple_of_32(gb, scene):
+    d_s, tree, hs, htree, rays = scene
+    out = torch.empty(33, dtype=torch.int32, device="cuda")
+    with pytest.raises(ValueError):           # bintree_trace.cuh:231-238
+        gb.trace_hitcounts_sph(dev(rays[:33]), d_s, tree, out)
