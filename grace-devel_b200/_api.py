@@ -24,12 +24,12 @@ __all__ = [
     "Tree", "RaySortType", "Octants", "N_table", "kernel_integral_table",
     "morton_keys_sph", "morton_keys30_sort_sph", "morton_keys63_sort_sph",
     "euclidean_deltas_sph", "surface_area_deltas_sph", "XOR_deltas_sph", "ALBVH_sph",
-    "trace_hitcounts_sph", "trace_cumulative_sph", "trace_sph", "trace_with_sentinels_sph",
+    "trace_hitcounts_sph", "trace_cumulative_sph", "trace_stats_sph", "trace_ray_cost_sph", "trace_sph", "trace_with_sentinels_sph",
     "sort_by_distance", "sort_by_key", "exclusive_scan",
     "min_vec3", "max_vec3", "min_max_x", "min_vec4", "max_vec4",
     "uniform_random_rays", "uniform_random_rays_single_octant", "one_to_many_rays",
     "plane_parallel_random_rays", "orthographic_projection_rays", "pinhole_camera_rays",
-    "healpix_rays", "synth_gadget_spheres", "context", "lib", "build_tree",
+    "healpix_rays", "synth_gadget_spheres", "context", "lib", "build_tree", "set_trace_mode",
 ]
 
 _c = ctypes
@@ -87,6 +87,7 @@ _t_cum = _sig("grace_b200_trace_cumulative_f4", [_P, _P, _sz, _P, _sz, _TS, _P, 
 _t_hcount = _sig("grace_b200_trace_hits_count_f4",
                  [_P, _P, _sz, _P, _sz, _TS, _c.c_int, _P, _c.POINTER(_c.c_longlong), _P])
 _t_hfill = _sig("grace_b200_trace_hits_fill_f4", [_P, _P, _sz, _P, _sz, _TS, _P, _P, _P, _P, _P])
+_t_stats = _sig("grace_b200_trace_stats_f4", [_P, _P, _sz, _P, _sz, _TS, _c.POINTER(_c.c_longlong * 4), _P])
 _sort_dist = _sig("grace_b200_sort_by_distance", [_P, _P, _P, _sz, _sz, _P, _P, _P])
 _scan = _sig("grace_b200_exclusive_scan_i32", [_P, _P, _P, _sz, _P, _P])
 _table = _sig("grace_b200_kernel_integral_table", [_c.POINTER(_c.c_int)], _c.POINTER(_c.c_double))
@@ -164,6 +165,12 @@ def _h3(v):
 
 def reserve(nbytes):
     _check(_reserve(context(), nbytes))
+
+
+def set_trace_mode(mode):
+    """'ray' (default: per-ray traversal, padded slab test) or 'packet' (the reference's
+    32-ray packet schedule)."""
+    _check(_sig("grace_b200_set_trace_mode", [_P, _c.c_int])(context(), {"ray": 0, "packet": 1}[mode]))
 
 
 def kernel_integral_table():
@@ -365,6 +372,24 @@ def trace_cumulative_sph(d_rays, d_spheres, d_tree, d_cumulated):
     _need(d_cumulated, torch.float32, "d_cumulated")
     assert d_cumulated.numel() >= d_rays.shape[0]
     _check(_t_cum(*_trace_args(d_rays, d_spheres, d_tree), _dp(d_cumulated), _stream()))
+
+
+def trace_stats_sph(d_rays, d_spheres, d_tree):
+    """Traversal counters of the packet algorithm: dict(node_visits, leaf_visits,
+    prims_staged, hits) summed over all packets (for the algorithmic-bytes figure)."""
+    out = (_c.c_longlong * 4)()
+    _check(_t_stats(*_trace_args(d_rays, d_spheres, d_tree), ctypes.byref(out), _stream()))
+    return dict(node_visits=out[0], leaf_visits=out[1], prims_staged=out[2], hits=out[3])
+
+
+def trace_ray_cost_sph(d_rays, d_spheres, d_tree):
+    """Diagnostic: (sphere tests, inner-node steps) per ray of the per-ray traversal."""
+    n = d_rays.shape[0]
+    tests = torch.empty(n, dtype=torch.int32, device=d_rays.device)
+    steps = torch.empty(n, dtype=torch.int32, device=d_rays.device)
+    fn = _sig("grace_b200_trace_ray_cost_f4", [_P, _P, _sz, _P, _sz, _TS, _P, _P, _P])
+    _check(fn(*_trace_args(d_rays, d_spheres, d_tree), _dp(tests), _dp(steps), _stream()))
+    return tests, steps
 
 
 def _trace_lists(d_rays, d_spheres, d_tree, d_ray_offsets, sentinels):

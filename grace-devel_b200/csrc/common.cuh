@@ -18,6 +18,7 @@ struct grace_b200_ctx {
     int* d_scalars = nullptr;  // small persistent device scalars (tickets, counts)
     int* h_pinned = nullptr;   // pinned host mirror for count read-backs
     int last_n_leaves_valid = 0;
+    int trace_mode = GRACE_B200_TRACE_PER_RAY;
 };
 
 // d_scalars layout (ints)

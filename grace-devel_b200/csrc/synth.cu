@@ -3,8 +3,10 @@
 // The reference ships no data file (its profilers default to a 128^3 Gadget-2 snapshot
 // that is not in the repository, tests/profile_tree_gadget/profile_tree_gadget.cu:35), so
 // the benchmark inputs are synthetic: float4 {x,y,z,h} in [0,1)^3, 30 %
-// uniform background + 70 % in 512 Plummer-profile halos (centres uniform, scale radii
-// log-uniform in [0.002, 0.02], masses from a power law), smoothing length from the
+// uniform background + 70 % in 512 Plummer-profile halos (centres uniform, masses from a
+// power law, scale radius set from the mass so that each halo's central density is
+// 10^3..10^4 times the mean -- the density contrast of a cosmological gas snapshot --
+// and clamped to [0.002, 0.03]), smoothing length from the
 // analytic local number density with N_ngb = 32, clamped to [1e-5, 0.1], particles stored
 // in Peano-Hilbert cell order at 2^7 cells per side (Gadget's on-disk order).
 // Counter-based hashing (Wang/Jenkins, the hash of tests/helper/random.cuh:20-29) makes
@@ -46,7 +48,6 @@ __global__ void make_halos_kernel(Halo* halos, unsigned seed)
     H.cx = u01(seed ^ 0xabcdu, h, 0);
     H.cy = u01(seed ^ 0xabcdu, h, 1);
     H.cz = u01(seed ^ 0xabcdu, h, 2);
-    H.a = 0.002f * powf(10.0f, u01(seed ^ 0xabcdu, h, 3));          // log-uniform [0.002, 0.02]
     const float um = u01(seed ^ 0xabcdu, h, 4);
     const float mass = powf(1.0f - um * 0.999f, -1.0f / 0.9f);        // power law dN/dm ~ m^-1.9
     m[h] = mass;
@@ -55,6 +56,11 @@ __global__ void make_halos_kernel(Halo* halos, unsigned seed)
     for (int i = 0; i < N_HALOS; ++i) { tot += m[i]; if (i <= h) cum += m[i]; }
     H.mass = mass / tot;
     H.cum_mass = cum / tot;
+    // central Plummer density 3 M / (4 pi a^3) = contrast * mean density, contrast log-uniform
+    // in [1e3, 1e4]; M = (1 - F_BACKGROUND) * mass fraction (in units of the total mass)
+    const float contrast = 1.0e3f * powf(10.0f, u01(seed ^ 0xabcdu, h, 3));
+    H.a = cbrtf(3.0f * (1.0f - F_BACKGROUND) * H.mass / (4.0f * 3.14159265f * contrast));
+    H.a = fminf(fmaxf(H.a, 0.002f), 0.03f);
     halos[h] = H;
 }
 

@@ -35,7 +35,7 @@ constexpr int TR_WARPS = TR_THREADS / 32;
 constexpr int TR_STACK = 96;             // reference STACK_SIZE is 64 (kernel_config.h:13)
 constexpr int N_TABLE = 51;
 
-enum { MODE_COUNT = 0, MODE_CUMULATIVE = 1, MODE_FILL = 2 };
+enum { MODE_COUNT = 0, MODE_CUMULATIVE = 1, MODE_FILL = 2, MODE_STATS = 3, MODE_RAYCOST = 4 };
 
 // Numeric data of cuda/trace_sph.cuh:32-48: line integrals of the Gadget-2 cubic
 // spline at impact parameter b/h = i/50.
@@ -138,7 +138,8 @@ trace_kernel(const grace_b200_ray* __restrict__ rays, int n_packets,
              int* __restrict__ out_counts, float* __restrict__ out_cum,
              const int* __restrict__ offsets, int* __restrict__ hit_idx,
              float* __restrict__ hit_integral, float* __restrict__ hit_dist,
-             int* __restrict__ packet_counter, int* __restrict__ err_flag)
+             int* __restrict__ packet_counter, int* __restrict__ err_flag,
+             unsigned long long* __restrict__ stats)
 {
     extern __shared__ __align__(16) unsigned char tr_smem[];
     // layout: [double table 51 (+pad)] [stacks TR_WARPS x TR_STACK int] [prims TR_WARPS x mpl float4]
@@ -147,7 +148,7 @@ trace_kernel(const grace_b200_ray* __restrict__ rays, int n_packets,
     float4* s_prims_all = (float4*)(s_stack_all + TR_WARPS * TR_STACK);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (MODE != MODE_COUNT) {
+    if (MODE == MODE_CUMULATIVE || MODE == MODE_FILL) {
         for (int i = threadIdx.x; i < N_TABLE; i += TR_THREADS) s_table[i] = c_kernel_table[i];
         __syncthreads();
     }
@@ -170,10 +171,12 @@ trace_kernel(const grace_b200_ray* __restrict__ rays, int n_packets,
         int cursor = 0;
         if (MODE == MODE_FILL) cursor = offsets[ray_index];
 
+        unsigned long long st_nodes = 0, st_leaves = 0, st_prims = 0;
         int sp = 0;            // number of entries below the register top
         int top = root;        // top of stack lives in a register; -1 = empty
         while (top >= 0) {
             if (top < n_nodes) {
+                if (MODE == MODE_STATS) ++st_nodes;
                 const int4* np = nodes + 4 * (size_t)top;
                 const int4 n0 = __ldg(np + 0);
                 const int4 n1 = __ldg(np + 1);
@@ -204,6 +207,7 @@ trace_kernel(const grace_b200_ray* __restrict__ rays, int n_packets,
             } else {
                 const int4 leaf = __ldg(leaves + (top - n_nodes));
                 top = sp > 0 ? stack[--sp] : -1;
+                if (MODE == MODE_STATS) { ++st_leaves; st_prims += leaf.y; }
                 for (int i = lane; i < leaf.y; i += 32) s_prims[i] = __ldg(spheres + leaf.x + i);
                 __syncwarp();
                 for (int i = 0; i < leaf.y; ++i) {
@@ -211,7 +215,7 @@ trace_kernel(const grace_b200_ray* __restrict__ rays, int n_packets,
                     float b2, dot;
                     if (sphere_test(s, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, ray.length,
                                     b2, dot)) {
-                        if (MODE == MODE_COUNT) {
+                        if (MODE == MODE_COUNT || MODE == MODE_STATS) {
                             ++count;
                         } else if (MODE == MODE_CUMULATIVE) {
                             cum = __fadd_rn(cum, kernel_integral(b2, s.w, s_table));
@@ -228,6 +232,161 @@ trace_kernel(const grace_b200_ray* __restrict__ rays, int n_packets,
         }
         if (MODE == MODE_COUNT) out_counts[ray_index] = count;
         if (MODE == MODE_CUMULATIVE) out_cum[ray_index] = cum;
+        if (MODE == MODE_STATS) {
+            unsigned hits = __reduce_add_sync(0xffffffffu, (unsigned)count);
+            if (lane == 0) {
+                atomicAdd(stats + 0, st_nodes);
+                atomicAdd(stats + 1, st_leaves);
+                atomicAdd(stats + 2, st_prims);
+                atomicAdd(stats + 3, (unsigned long long)hits);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Per-ray traversal (default).
+//
+// Every (ray, sphere) pair whose sphere_test() is true must be found; which OTHER pairs
+// get tested is free.  The reference's packet rule (test a leaf on all 32 lanes if any
+// lane's slab test reaches it) makes one beam that engulfs a dense halo test every
+// particle in it on every lane -- measured on the 2^24-particle workload: 11.3k tests per
+// ray for 1.3k hits, and a few such packets keep 83 % of the SMs idle at the tail.
+// Here each lane walks the tree for its own ray with a slab test against boxes PADDED by
+// pad = 64 * 2^-24 * (|ox|+|oy|+|oz|+len).  The padding exceeds every rounding error of
+// sphere_test() and of the slab arithmetic (DESIGN.md "conservative slab test"), so a
+// sphere that sphere_test() accepts always lies in a visited leaf: the hit set equals the
+// brute-force set the reference's own test demands (tests/tree_traversal/tree_traversal.cu:
+// 65-121), independent of how rays are grouped.  Left-first depth-first order visits
+// leaves, hence primitives, in ascending index order -- the same order in which the
+// reference accumulates -- so column densities and hit lists are bit-identical too.
+//
+// Stack: 32 entries per lane in shared memory laid out [depth][thread] (bank == lane,
+// conflict-free at any mix of depths), deeper levels spill to a local array.
+// ---------------------------------------------------------------------------
+constexpr int RT_THREADS = 128;
+constexpr int RT_SMEM_DEPTH = 32;
+constexpr int RT_LOCAL_DEPTH = 64;
+
+__device__ __forceinline__ bool slab_hit_padded(float bx, float tx, float by, float ty, float bz, float tz,
+                                                float lox, float loy, float loz,   // o + pad
+                                                float hix, float hiy, float hiz,   // o - pad
+                                                float ix, float iy, float iz, float len)
+{
+    const float tbx = (bx - lox) * ix, ttx = (tx - hix) * ix;
+    const float tby = (by - loy) * iy, tty = (ty - hiy) * iy;
+    const float tbz = (bz - loz) * iz, ttz = (tz - hiz) * iz;
+    const float tmin = fmaxf(fmaxf(fminf(tbx, ttx), fminf(tby, tty)), fmaxf(fminf(tbz, ttz), 0.0f));
+    const float tmax = fminf(fminf(fmaxf(tbx, ttx), fmaxf(tby, tty)), fminf(fmaxf(tbz, ttz), len));
+    return tmax >= tmin;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(RT_THREADS)
+trace_ray_kernel(const grace_b200_ray* __restrict__ rays, int n_packets,
+                 const float4* __restrict__ spheres,
+                 const int4* __restrict__ nodes, const int4* __restrict__ leaves,
+                 int n_nodes, const int* __restrict__ root_ptr,
+                 int* __restrict__ out_counts, float* __restrict__ out_cum,
+                 const int* __restrict__ offsets, int* __restrict__ hit_idx,
+                 float* __restrict__ hit_integral, float* __restrict__ hit_dist,
+                 int* __restrict__ packet_counter, int* __restrict__ err_flag)
+{
+    __shared__ double s_table[52];
+    __shared__ int s_stack[RT_SMEM_DEPTH * RT_THREADS];
+    const int lane = threadIdx.x & 31;
+    if (MODE == MODE_CUMULATIVE || MODE == MODE_FILL) {
+        for (int i = threadIdx.x; i < N_TABLE; i += RT_THREADS) s_table[i] = c_kernel_table[i];
+        __syncthreads();
+    }
+    int* my_stack = s_stack + threadIdx.x;
+    int lstack[RT_LOCAL_DEPTH];
+    const int root = __ldg(root_ptr);
+
+    for (;;) {
+        int packet = 0;
+        if (lane == 0) packet = atomicAdd(packet_counter, 1);
+        packet = __shfl_sync(0xffffffffu, packet, 0);
+        if (packet >= n_packets) break;
+        const int ray_index = packet * 32 + lane;
+        const grace_b200_ray ray = rays[ray_index];
+        const float ix = __fdiv_rn(1.0f, ray.dx), iy = __fdiv_rn(1.0f, ray.dy),
+                    iz = __fdiv_rn(1.0f, ray.dz);
+        const float pad = 64.0f * 5.9604645e-8f * (fabsf(ray.ox) + fabsf(ray.oy) + fabsf(ray.oz) + fabsf(ray.length));
+        const float lox = ray.ox + pad, loy = ray.oy + pad, loz = ray.oz + pad;
+        const float hix = ray.ox - pad, hiy = ray.oy - pad, hiz = ray.oz - pad;
+        int count = 0;
+        float cum = 0.0f;
+        int cursor = 0;
+        if (MODE == MODE_FILL) cursor = offsets[ray_index];
+
+        int sp = 0;
+        int cur = root;
+        while (cur >= 0) {
+            // ---- inner nodes ----
+            while ((unsigned)cur < (unsigned)n_nodes) {
+                if (MODE == MODE_RAYCOST) ++cursor;      // node steps
+                const int4* np = nodes + 4 * (size_t)cur;
+                const int4 n0 = __ldg(np + 0);
+                const int4 n1 = __ldg(np + 1);
+                const int4 n2 = __ldg(np + 2);
+                const int4 n3 = __ldg(np + 3);
+                const bool hitL = slab_hit_padded(__int_as_float(n1.x), __int_as_float(n1.y),
+                                                  __int_as_float(n1.z), __int_as_float(n1.w),
+                                                  __int_as_float(n3.x), __int_as_float(n3.y),
+                                                  lox, loy, loz, hix, hiy, hiz, ix, iy, iz, ray.length);
+                const bool hitR = slab_hit_padded(__int_as_float(n2.x), __int_as_float(n2.y),
+                                                  __int_as_float(n2.z), __int_as_float(n2.w),
+                                                  __int_as_float(n3.z), __int_as_float(n3.w),
+                                                  lox, loy, loz, hix, hiy, hiz, ix, iy, iz, ray.length);
+                if (hitL) {
+                    if (hitR) {          // push right, descend left
+                        if (sp < RT_SMEM_DEPTH) my_stack[sp * RT_THREADS] = n0.y;
+                        else if (sp < RT_SMEM_DEPTH + RT_LOCAL_DEPTH) lstack[sp - RT_SMEM_DEPTH] = n0.y;
+                        else { *err_flag = 1; }
+                        ++sp;
+                    }
+                    cur = n0.x;
+                } else if (hitR) {
+                    cur = n0.y;
+                } else {
+                    if (sp > 0) {
+                        --sp;
+                        cur = sp < RT_SMEM_DEPTH ? my_stack[sp * RT_THREADS]
+                                                 : lstack[min(sp - RT_SMEM_DEPTH, RT_LOCAL_DEPTH - 1)];
+                    } else cur = -1;
+                }
+            }
+            // ---- leaf ----
+            if (cur >= n_nodes) {
+                const int2 leaf = __ldg((const int2*)(leaves + (cur - n_nodes)));
+                if (MODE == MODE_RAYCOST) count += leaf.y;   // sphere tests
+                for (int i = 0; i < leaf.y && MODE != MODE_RAYCOST; ++i) {
+                    const float4 s = __ldg(spheres + leaf.x + i);
+                    float b2, dot;
+                    if (sphere_test(s, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, ray.length, b2, dot)) {
+                        if (MODE == MODE_COUNT) {
+                            ++count;
+                        } else if (MODE == MODE_CUMULATIVE) {
+                            cum = __fadd_rn(cum, kernel_integral(b2, s.w, s_table));
+                        } else {
+                            hit_idx[cursor] = leaf.x + i;
+                            hit_integral[cursor] = kernel_integral(b2, s.w, s_table);
+                            hit_dist[cursor] = dot;
+                            ++cursor;
+                        }
+                    }
+                }
+                if (sp > 0) {
+                    --sp;
+                    cur = sp < RT_SMEM_DEPTH ? my_stack[sp * RT_THREADS]
+                                             : lstack[min(sp - RT_SMEM_DEPTH, RT_LOCAL_DEPTH - 1)];
+                } else cur = -1;
+            }
+        }
+        if (MODE == MODE_COUNT) out_counts[ray_index] = count;
+        if (MODE == MODE_CUMULATIVE) out_cum[ray_index] = cum;
+        if (MODE == MODE_RAYCOST) { out_counts[ray_index] = count; hit_idx[ray_index] = cursor; }
     }
 }
 
@@ -241,7 +400,8 @@ template <int MODE>
 int launch_trace(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, size_t n_rays,
                  const float* d_spheres4, size_t n, const grace_b200_tree* tree,
                  int* out_counts, float* out_cum, const int* offsets, int* hit_idx,
-                 float* hit_integral, float* hit_dist, cudaStream_t st)
+                 float* hit_integral, float* hit_dist, cudaStream_t st,
+                 unsigned long long* d_stats = nullptr)
 {
     GB_REQUIRE(ctx && d_rays && d_spheres4 && tree && tree->d_nodes && tree->d_leaves && tree->d_root,
                GRACE_B200_EINVAL, "NULL argument");
@@ -253,6 +413,23 @@ int launch_trace(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, size_t n_ray
     (void)n;
     if (n_rays == 0) return GRACE_B200_OK;
     const int n_packets = (int)(n_rays / 32);
+    int* counter = ctx->d_scalars + GB_SC_TRACE_CTR;
+    if (MODE == MODE_RAYCOST || (MODE != MODE_STATS && ctx->trace_mode == GRACE_B200_TRACE_PER_RAY)) {
+        int per_sm = 0;
+        GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_ray_kernel<MODE>, RT_THREADS, 0));
+        if (per_sm < 1) per_sm = 1;
+        int blocks = ctx->sm_count * per_sm;
+        const int need = (n_packets + RT_THREADS / 32 - 1) / (RT_THREADS / 32);
+        if (blocks > need) blocks = need;
+        GB_CUDA(cudaMemsetAsync(counter, 0, 2 * sizeof(int), st));
+        trace_ray_kernel<MODE><<<blocks, RT_THREADS, 0, st>>>(
+            d_rays, n_packets, (const float4*)d_spheres4, (const int4*)tree->d_nodes,
+            (const int4*)tree->d_leaves, tree->n_leaves - 1, tree->d_root,
+            out_counts, out_cum, offsets, hit_idx, hit_integral, hit_dist, counter,
+            ctx->d_scalars + GB_SC_ERRFLAG);
+        GB_LAUNCH_CHECK();
+        return GRACE_B200_OK;
+    }
     const size_t smem = trace_smem_bytes(tree->max_per_leaf);
     GB_REQUIRE(smem <= 200 * 1024, GRACE_B200_EINVAL, "max_per_leaf too large for shared memory staging");
     GB_CUDA(cudaFuncSetAttribute(trace_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -262,13 +439,12 @@ int launch_trace(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, size_t n_ray
     int blocks = ctx->sm_count * per_sm;
     const int need = (n_packets + TR_WARPS - 1) / TR_WARPS;
     if (blocks > need) blocks = need;
-    int* counter = ctx->d_scalars + GB_SC_TRACE_CTR;
     GB_CUDA(cudaMemsetAsync(counter, 0, 2 * sizeof(int), st));   // counter + error flag
     trace_kernel<MODE><<<blocks, TR_THREADS, smem, st>>>(
         d_rays, n_packets, (const float4*)d_spheres4, (const int4*)tree->d_nodes,
         (const int4*)tree->d_leaves, tree->n_leaves - 1, tree->d_root, tree->max_per_leaf,
         out_counts, out_cum, offsets, hit_idx, hit_integral, hit_dist, counter,
-        ctx->d_scalars + GB_SC_ERRFLAG);
+        ctx->d_scalars + GB_SC_ERRFLAG, d_stats);
     GB_LAUNCH_CHECK();
     return GRACE_B200_OK;
 }
@@ -276,6 +452,15 @@ int launch_trace(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, size_t n_ray
 } // namespace
 
 extern "C" {
+
+int grace_b200_set_trace_mode(grace_b200_ctx* ctx, int mode)
+{
+    GB_REQUIRE(ctx, GRACE_B200_EINVAL, "ctx is NULL");
+    GB_REQUIRE(mode == GRACE_B200_TRACE_PER_RAY || mode == GRACE_B200_TRACE_PACKET, GRACE_B200_EINVAL,
+               "unknown trace mode %d", mode);
+    ctx->trace_mode = mode;
+    return GRACE_B200_OK;
+}
 
 const double* grace_b200_kernel_integral_table(int* n_table)
 {
@@ -300,6 +485,32 @@ int grace_b200_trace_cumulative_f4(grace_b200_ctx* ctx, const grace_b200_ray* d_
     return launch_trace<MODE_CUMULATIVE>(ctx, d_rays, n_rays, d_spheres4, n, tree, nullptr,
                                          d_cumulated, nullptr, nullptr, nullptr, nullptr,
                                          (cudaStream_t)stream);
+}
+
+int grace_b200_trace_stats_f4(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, size_t n_rays,
+                              const float* d_spheres4, size_t n, const grace_b200_tree* tree,
+                              long long* h_stats4, void* stream)
+{
+    GB_REQUIRE(ctx && h_stats4, GRACE_B200_EINVAL, "NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long* d_stats = (unsigned long long*)gb_workspace(ctx, 256);
+    if (!d_stats) return GRACE_B200_ENOMEM;
+    GB_CUDA(cudaMemsetAsync(d_stats, 0, 4 * sizeof(unsigned long long), st));
+    int rc = launch_trace<MODE_STATS>(ctx, d_rays, n_rays, d_spheres4, n, tree, nullptr, nullptr,
+                                      nullptr, nullptr, nullptr, nullptr, st, d_stats);
+    if (rc) return rc;
+    GB_CUDA(cudaMemcpyAsync(h_stats4, d_stats, 4 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    GB_CUDA(cudaStreamSynchronize(st));
+    return GRACE_B200_OK;
+}
+
+int grace_b200_trace_ray_cost_f4(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, size_t n_rays,
+                                 const float* d_spheres4, size_t n, const grace_b200_tree* tree,
+                                 int* d_sphere_tests, int* d_node_steps, void* stream)
+{
+    GB_REQUIRE(d_sphere_tests && d_node_steps, GRACE_B200_EINVAL, "NULL output");
+    return launch_trace<MODE_RAYCOST>(ctx, d_rays, n_rays, d_spheres4, n, tree, d_sphere_tests, nullptr,
+                                      nullptr, d_node_steps, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 int grace_b200_trace_hits_fill_f4(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, size_t n_rays,

@@ -151,6 +151,16 @@ typedef struct {
     int max_per_leaf;
 } grace_b200_tree;
 
+/* Traversal schedule.  PER_RAY (default): every lane walks the tree for its own ray with a
+ * conservatively padded slab test; the hit set is exactly the brute-force set.  PACKET:
+ * the reference's schedule (cuda/kernels/bintree_trace.cuh:119-193: 32 consecutive rays
+ * share one stack, a node is entered if ANY lane hits it), kept for A/B measurements and
+ * for the traversal counters.  Both give identical results wherever the reference passes
+ * its own brute-force test (tests/tree_traversal/tree_traversal.cu:84-121). */
+#define GRACE_B200_TRACE_PER_RAY 0
+#define GRACE_B200_TRACE_PACKET  1
+int grace_b200_set_trace_mode(grace_b200_ctx* ctx, int mode);
+
 /* All trace calls return GRACE_B200_EINVAL unless n_rays % 32 == 0
  * (bintree_trace.cuh:231-238): a packet is 32 consecutive rays. */
 
@@ -181,6 +191,19 @@ int grace_b200_trace_hits_fill_f4(grace_b200_ctx* ctx, const grace_b200_ray* d_r
                                   const grace_b200_tree* tree, const int* d_ray_offsets,
                                   int* d_hit_indices, float* d_hit_integrals,
                                   float* d_hit_distances, void* stream);
+
+/* Traversal counters of the reference packet algorithm on these inputs (no reference
+ * counterpart; used for the algorithmic-bytes figure):
+ * h_stats4 = {inner-node visits, leaf visits, primitives staged, ray-sphere hits},
+ * summed over all packets.  Synchronises the stream. */
+int grace_b200_trace_stats_f4(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, size_t n_rays,
+                              const float* d_spheres4, size_t n, const grace_b200_tree* tree,
+                              long long* h_stats4, void* stream);
+
+/* Diagnostic: per-ray cost of the per-ray traversal (sphere tests and inner-node steps). */
+int grace_b200_trace_ray_cost_f4(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, size_t n_rays,
+                                 const float* d_spheres4, size_t n, const grace_b200_tree* tree,
+                                 int* d_sphere_tests, int* d_node_steps, void* stream);
 
 /* replaces: sort_by_distance (cuda/sort.cuh:100-131 -> sgpu::SegSortPairsFromIndices,
  *   external/sgpu/kernels/segmentedsort.cuh:732-779, + two order_by_index gathers).

@@ -188,6 +188,14 @@ def test_tree_tiny_and_errors(gb, orc):
 
 
 # ----------------------------------------------------------------------------- trace
+@pytest.fixture(params=["ray", "packet"], autouse=True)
+def trace_mode(request, gb):
+    """Every test below runs under both traversal schedules."""
+    gb.set_trace_mode(request.param)
+    yield request.param
+    gb.set_trace_mode("ray")
+
+
 @pytest.fixture(scope="module")
 def scene(gb, orc):
     s = clustered_spheres(1 << 17, seed=3)
@@ -204,6 +212,18 @@ def test_hitcounts_exact(gb, orc, scene):
     assert np.array_equal(host(out), ref)
     sub = slice(0, 256)
     assert np.array_equal(host(out)[sub], orc.brute_hitcounts(rays[sub], hs))
+
+
+def test_traversal_counters_match_oracle(gb, orc, scene):
+    # the algorithmic-bytes figure of bench.py rests on these counters
+    d_s, tree, hs, htree, rays = scene
+    st = gb.trace_stats_sph(dev(rays), d_s, tree)
+    counts, stats, depth = orc.trace(rays, hs, htree, 0, with_stats=True)
+    assert st["node_visits"] == int(stats[:, 0].sum())
+    assert st["leaf_visits"] == int(stats[:, 1].sum())
+    assert st["prims_staged"] == int(stats[:, 2].sum())
+    assert st["hits"] == int(counts.sum())
+    assert depth <= 64          # reference STACK_SIZE (kernel_config.h:13)
 
 
 def test_hitcounts_config1(gb, orc):
@@ -284,7 +304,7 @@ def test_segsort_all_classes(gb, orc):
 def test_exclusive_scan(gb):
     rng = np.random.default_rng(0)
     for n in (1, 2047, 2048, 2049, 1000003):
-        a = rng.integers(0, 5000, n).astype(np.int32)
+        a = rng.integers(0, 2000, n).astype(np.int32)      # total < 2^31
         out, total = gb.exclusive_scan(dev(a))
         ref = np.concatenate([[0], np.cumsum(a[:-1], dtype=np.int64)])
         assert np.array_equal(host(out).astype(np.int64), ref)
