@@ -24,12 +24,12 @@ __all__ = [
     "Tree", "RaySortType", "Octants", "N_table", "kernel_integral_table",
     "morton_keys_sph", "morton_keys30_sort_sph", "morton_keys63_sort_sph",
     "euclidean_deltas_sph", "surface_area_deltas_sph", "XOR_deltas_sph", "ALBVH_sph",
-    "trace_hitcounts_sph", "trace_cumulative_sph", "trace_stats_sph", "trace_ray_cost_sph", "trace_sph", "trace_with_sentinels_sph",
+    "trace_hitcounts_sph", "trace_cumulative_sph", "trace_stats_sph", "trace_ray_cost_sph", "trace_packet_profile_sph", "trace_sph", "trace_with_sentinels_sph",
     "sort_by_distance", "sort_by_key", "exclusive_scan",
     "min_vec3", "max_vec3", "min_max_x", "min_vec4", "max_vec4",
     "uniform_random_rays", "uniform_random_rays_single_octant", "one_to_many_rays",
     "plane_parallel_random_rays", "orthographic_projection_rays", "pinhole_camera_rays",
-    "healpix_rays", "synth_gadget_spheres", "context", "lib", "build_tree", "set_trace_mode",
+    "healpix_rays", "synth_gadget_spheres", "context", "lib", "build_tree", "set_trace_mode", "set_trace_budget", "device_error",
 ]
 
 _c = ctypes
@@ -168,9 +168,22 @@ def reserve(nbytes):
 
 
 def set_trace_mode(mode):
-    """'ray' (default: per-ray traversal, padded slab test) or 'packet' (the reference's
-    32-ray packet schedule)."""
-    _check(_sig("grace_b200_set_trace_mode", [_P, _c.c_int])(context(), {"ray": 0, "packet": 1}[mode]))
+    """'packet' (default), 'ray' (per-ray traversal) or 'packet_ref' (the reference's
+    schedule and slab arithmetic bit for bit); see include/grace_b200.h."""
+    _check(_sig("grace_b200_set_trace_mode", [_P, _c.c_int])(
+        context(), {"ray": 0, "packet": 1, "packet_ref": 2}[mode]))
+
+
+def set_trace_budget(steps):
+    """Traversal steps before a packet may be split into ray-subset tasks (0 = never)."""
+    _check(_sig("grace_b200_set_trace_budget", [_P, _c.c_int])(context(), int(steps)))
+
+
+def device_error():
+    """Error flag of the last trace launch (0 ok, 1 stack overflow, 2 runaway traversal)."""
+    f = _c.c_int(0)
+    _check(_sig("grace_b200_device_error", [_P, _c.POINTER(_c.c_int), _P])(context(), ctypes.byref(f), _stream()))
+    return f.value
 
 
 def kernel_integral_table():
@@ -380,6 +393,18 @@ def trace_stats_sph(d_rays, d_spheres, d_tree):
     out = (_c.c_longlong * 4)()
     _check(_t_stats(*_trace_args(d_rays, d_spheres, d_tree), ctypes.byref(out), _stream()))
     return dict(node_visits=out[0], leaf_visits=out[1], prims_staged=out[2], hits=out[3])
+
+
+def trace_packet_profile_sph(d_rays, d_spheres, d_tree):
+    """Diagnostic: work counters of the production packet kernel."""
+    import numpy as np
+    npk = d_rays.shape[0] // 32
+    out = np.zeros(4 + 4 * npk, np.int64)
+    cnt = torch.empty(d_rays.shape[0], dtype=torch.int32, device=d_rays.device)
+    fn = _sig("grace_b200_trace_packet_profile_f4", [_P, _P, _sz, _P, _sz, _TS, _P, _P, _c.c_int, _P])
+    _check(fn(*_trace_args(d_rays, d_spheres, d_tree), _dp(cnt), out.ctypes.data_as(_P), 1, _stream()))
+    return dict(node_steps=int(out[0]), leaf_visits=int(out[1]), prims_staged=int(out[2]),
+                prims_kept=int(out[3]), per_packet=out[4:].reshape(npk, 4))
 
 
 def trace_ray_cost_sph(d_rays, d_spheres, d_tree):

@@ -18,7 +18,8 @@ struct grace_b200_ctx {
     int* d_scalars = nullptr;  // small persistent device scalars (tickets, counts)
     int* h_pinned = nullptr;   // pinned host mirror for count read-backs
     int last_n_leaves_valid = 0;
-    int trace_mode = GRACE_B200_TRACE_PER_RAY;
+    int trace_mode = GRACE_B200_TRACE_PACKET;
+    int trace_budget = 2048;   // traversal steps before a packet may be split (0 = never)
 };
 
 // d_scalars layout (ints)
@@ -29,6 +30,7 @@ enum {
     GB_SC_TRACE_CTR = 4,    // packet scheduler counter
     GB_SC_ERRFLAG = 5,      // device-side error flag (trace stack overflow)
     GB_SC_TOTAL64 = 8,      // 64-bit total (2 ints), 8-byte aligned
+    GB_SC_TASKS = 32,       // trace load balancing: record count + two task-list counts
     GB_SC_CLASS = 16,       // segmented sort class counters (8 ints) + XL total (2 ints)
     GB_SC_COUNT = 64
 };

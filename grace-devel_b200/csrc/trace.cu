@@ -28,6 +28,8 @@
 
 #include <math_constants.h>
 
+#include <algorithm>
+
 namespace {
 
 constexpr int TR_THREADS = 128;          // 4 packets per CTA
@@ -390,10 +392,79 @@ trace_ray_kernel(const grace_b200_ray* __restrict__ rays, int n_packets,
     }
 }
 
+#include "trace_packet.cuh"
+
 size_t trace_smem_bytes(int max_per_leaf)
 {
     return 52 * sizeof(double) + (size_t)TR_WARPS * TR_STACK * sizeof(int) +
            (size_t)TR_WARPS * max_per_leaf * sizeof(float4);
+}
+
+template <int MODE, int M4>
+int launch_packet(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, int n_packets,
+                  const float* d_spheres4, const grace_b200_tree* tree, int* out_counts,
+                  float* out_cum, const int* offsets, int* hit_idx, float* hit_integral,
+                  float* hit_dist, cudaStream_t st, unsigned long long* d_prof)
+{
+    if (MODE == MODE_STATS || MODE == MODE_RAYCOST) return GRACE_B200_EINVAL;   // other kernels
+    constexpr int KMODE = (MODE == MODE_STATS || MODE == MODE_RAYCOST) ? MODE_COUNT : MODE;
+    auto kernel = trace_packet_kernel<KMODE, M4>;
+    constexpr size_t psmem = packet_smem_bytes<KMODE, M4>();
+    GB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+    int per_sm = 0;
+    GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, PK_THREADS, psmem));
+    if (per_sm < 1) per_sm = 1;
+    const int full_grid = ctx->sm_count * per_sm;
+    int blocks = full_grid;
+    const int need = (n_packets + PK_WARPS - 1) / PK_WARPS;
+    if (blocks > need) blocks = need;
+    int* counter = ctx->d_scalars + GB_SC_TRACE_CTR;
+    // Load balancing rounds: 0 = packets, then suspended traversals resumed as tasks over
+    // 8, 2 and finally 1 ray(s); the last round runs to completion.  Rounds with nothing to
+    // do cost one empty launch.  Disabled (single round) for the profile counters.
+    const bool split = (d_prof == nullptr) && ctx->trace_budget > 0 && n_packets >= 64;
+    const int records_cap = split ? (int)std::min<size_t>(std::max<size_t>((size_t)n_packets / 4, 1024), 32768) : 0;
+    const int tasks_cap = 4 * records_cap;
+    int* records = nullptr;
+    int2* lists[2] = { nullptr, nullptr };
+    if (split) {
+        const size_t rec_bytes = gb_align((size_t)records_cap * PK_REC_WORDS * 4);
+        const size_t list_bytes = gb_align((size_t)tasks_cap * 8);
+        char* w = (char*)gb_workspace(ctx, 4096 + rec_bytes + 2 * list_bytes);
+        if (!w) return GRACE_B200_ENOMEM;
+        records = (int*)(w + 4096);
+        lists[0] = (int2*)(w + 4096 + rec_bytes);
+        lists[1] = (int2*)(w + 4096 + rec_bytes + list_bytes);
+    }
+    int* n_counts = ctx->d_scalars + GB_SC_TASKS;      // [0] records, [1] list 0, [2] list 1
+    if (split) GB_CUDA(cudaMemsetAsync(n_counts, 0, 4 * sizeof(int), st));
+    GB_CUDA(cudaMemsetAsync(ctx->d_scalars + GB_SC_ERRFLAG, 0, sizeof(int), st));
+    PkArgs P;
+    P.rays = d_rays; P.n_packets = n_packets; P.spheres = (const float4*)d_spheres4;
+    P.nodes = (const int4*)tree->d_nodes; P.leaves = (const int4*)tree->d_leaves;
+    P.n_nodes = tree->n_leaves - 1; P.root_ptr = tree->d_root;
+    P.out_counts = out_counts; P.out_cum = out_cum; P.offsets = offsets;
+    P.hit_idx = hit_idx; P.hit_integral = hit_integral; P.hit_dist = hit_dist;
+    P.unit_counter = counter; P.err_flag = ctx->d_scalars + GB_SC_ERRFLAG; P.prof = d_prof;
+    const int widths[3] = { 8, 2, 1 };
+    const int n_rounds = split ? 4 : 1;
+    for (int round = 0; round < n_rounds; ++round) {
+        PkTasks T = {};
+        if (split) {
+            T.records = records; T.n_records = n_counts; T.records_cap = records_cap; T.tasks_cap = tasks_cap;
+            T.budget = ctx->trace_budget;
+            if (round > 0) { T.tasks_in = lists[(round - 1) & 1]; T.n_tasks_in = n_counts + 1 + ((round - 1) & 1); }
+            if (round < n_rounds - 1) {
+                T.tasks_out = lists[round & 1]; T.n_tasks_out = n_counts + 1 + (round & 1);
+                T.child_width = widths[round];
+                if (round >= 2) GB_CUDA(cudaMemsetAsync(T.n_tasks_out, 0, sizeof(int), st));   // list reuse
+            }
+        }
+        GB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
+        kernel<<<round == 0 ? blocks : full_grid, PK_THREADS, psmem, st>>>(P, T);
+        GB_LAUNCH_CHECK();
+    }
+    return GRACE_B200_OK;
 }
 
 template <int MODE>
@@ -430,6 +501,17 @@ int launch_trace(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, size_t n_ray
         GB_LAUNCH_CHECK();
         return GRACE_B200_OK;
     }
+    if (MODE != MODE_STATS && MODE != MODE_RAYCOST && ctx->trace_mode == GRACE_B200_TRACE_PACKET &&
+        tree->max_per_leaf <= 128) {
+        if (tree->max_per_leaf <= 32)
+            return launch_packet<MODE, 32>(ctx, d_rays, n_packets, d_spheres4, tree, out_counts, out_cum,
+                                           offsets, hit_idx, hit_integral, hit_dist, st, d_stats);
+        if (tree->max_per_leaf <= 64)
+            return launch_packet<MODE, 64>(ctx, d_rays, n_packets, d_spheres4, tree, out_counts, out_cum,
+                                           offsets, hit_idx, hit_integral, hit_dist, st, d_stats);
+        return launch_packet<MODE, 128>(ctx, d_rays, n_packets, d_spheres4, tree, out_counts, out_cum,
+                                        offsets, hit_idx, hit_integral, hit_dist, st, d_stats);
+    }
     const size_t smem = trace_smem_bytes(tree->max_per_leaf);
     GB_REQUIRE(smem <= 200 * 1024, GRACE_B200_EINVAL, "max_per_leaf too large for shared memory staging");
     GB_CUDA(cudaFuncSetAttribute(trace_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -453,10 +535,28 @@ int launch_trace(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, size_t n_ray
 
 extern "C" {
 
+int grace_b200_device_error(grace_b200_ctx* ctx, int* h_flag, void* stream)
+{
+    GB_REQUIRE(ctx && h_flag, GRACE_B200_EINVAL, "NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    GB_CUDA(cudaMemcpyAsync(ctx->h_pinned + GB_SC_ERRFLAG, ctx->d_scalars + GB_SC_ERRFLAG, sizeof(int),
+                            cudaMemcpyDeviceToHost, st));
+    GB_CUDA(cudaStreamSynchronize(st));
+    *h_flag = ctx->h_pinned[GB_SC_ERRFLAG];
+    return GRACE_B200_OK;
+}
+
+int grace_b200_set_trace_budget(grace_b200_ctx* ctx, int steps)
+{
+    GB_REQUIRE(ctx && steps >= 0, GRACE_B200_EINVAL, "bad argument");
+    ctx->trace_budget = steps;
+    return GRACE_B200_OK;
+}
+
 int grace_b200_set_trace_mode(grace_b200_ctx* ctx, int mode)
 {
     GB_REQUIRE(ctx, GRACE_B200_EINVAL, "ctx is NULL");
-    GB_REQUIRE(mode == GRACE_B200_TRACE_PER_RAY || mode == GRACE_B200_TRACE_PACKET, GRACE_B200_EINVAL,
+    GB_REQUIRE(mode == GRACE_B200_TRACE_PER_RAY || mode == GRACE_B200_TRACE_PACKET || mode == GRACE_B200_TRACE_PACKET_REF, GRACE_B200_EINVAL,
                "unknown trace mode %d", mode);
     ctx->trace_mode = mode;
     return GRACE_B200_OK;
@@ -500,6 +600,29 @@ int grace_b200_trace_stats_f4(grace_b200_ctx* ctx, const grace_b200_ray* d_rays,
                                       nullptr, nullptr, nullptr, nullptr, st, d_stats);
     if (rc) return rc;
     GB_CUDA(cudaMemcpyAsync(h_stats4, d_stats, 4 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    GB_CUDA(cudaStreamSynchronize(st));
+    return GRACE_B200_OK;
+}
+
+int grace_b200_trace_packet_profile_f4(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, size_t n_rays,
+                                       const float* d_spheres4, size_t n, const grace_b200_tree* tree,
+                                       int* d_hit_counts, long long* h_prof4, int h_per_packet,
+                                       void* stream)
+{
+    GB_REQUIRE(ctx && h_prof4 && d_hit_counts, GRACE_B200_EINVAL, "NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t prof_words = 4 + 4 * (n_rays / 32);
+    unsigned long long* d_prof = (unsigned long long*)gb_workspace(ctx, prof_words * 8 + 256);
+    if (!d_prof) return GRACE_B200_ENOMEM;
+    GB_CUDA(cudaMemsetAsync(d_prof, 0, prof_words * 8, st));
+    const int saved = ctx->trace_mode;
+    ctx->trace_mode = GRACE_B200_TRACE_PACKET;
+    int rc = launch_trace<MODE_COUNT>(ctx, d_rays, n_rays, d_spheres4, n, tree, d_hit_counts, nullptr,
+                                      nullptr, nullptr, nullptr, nullptr, st, d_prof);
+    ctx->trace_mode = saved;
+    if (rc) return rc;
+    GB_CUDA(cudaMemcpyAsync(h_prof4, d_prof, (h_per_packet ? prof_words : 4) * sizeof(long long),
+                            cudaMemcpyDeviceToHost, st));
     GB_CUDA(cudaStreamSynchronize(st));
     return GRACE_B200_OK;
 }

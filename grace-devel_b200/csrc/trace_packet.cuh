@@ -1,0 +1,585 @@
+// trace_packet.cuh -- the production packet traversal kernel (included by trace.cu).
+//
+// Same packet structure as the reference (gpu::trace_kernel, cuda/kernels/bintree_trace.cuh:
+// 52-197: 32 consecutive rays share one traversal, a child is entered if ANY lane's slab test
+// reaches it) because rays of a packet overlap heavily -- measured on the 2^24-particle
+// workload: a leaf visited by a packet is needed by ~21 of its 32 rays -- so node fetches and
+// leaf staging are shared 32 ways.  What changes is where the cycles go:
+//
+//   * slab test against boxes padded by 64 ulp of the ray's coordinate scale, evaluated as
+//     t = fma(plane, 1/d, -(o -/+ pad)/d).  Padding makes the visited set a superset of every
+//     leaf holding a sphere that sphere_test() accepts (DESIGN.md "conservative slab test"),
+//     so the hit set is exactly the brute-force set the reference's own test demands;
+//   * per-lane hit masks travel with the traversal stack, so every leaf knows which rays can
+//     touch it;
+//   * memory-level parallelism: the walk first collects the next PK_BATCH leaves, fetches
+//     their records in one round trip and streams all their spheres into shared memory with
+//     cp.async in another, instead of three dependent round trips per leaf;
+//   * at staging, spheres that no ray of the packet can hit (outside a conservative
+//     cone/cylinder around the packet) are dropped and the rest compacted; the staging lane
+//     precomputes h*h, 1/h (IEEE) and, when all 32 rays share one origin, c - o;
+//   * dense leaves (many rays, few spheres): every lane tests every staged sphere;
+//     sparse leaves (few rays, many spheres): the work is transposed -- lane j holds sphere
+//     j and the few active rays are visited one by one;
+//   * the on-hit work (sqrt, double-precision table lerp) is not done in the test loop,
+//     where it would run on ~1 lane in 9: hits go to a per-lane FIFO in shared memory and
+//     are evaluated in batches.  FIFO order keeps each ray's accumulation in ascending
+//     primitive order, so sums are bit-identical to the reference's;
+//   * load balance: a packet that exceeds a step budget saves its state and is resumed, in
+//     a follow-up launch, as several tasks over disjoint subsets of its rays (PkTasks).
+//
+// All shared-memory addresses are compile-time offsets of one per-warp struct (the first
+// version derived them from the runtime max_per_leaf and ptxas re-derived them inside the
+// hot loops: 18 integer instructions per test iteration).
+#pragma once
+
+constexpr int PK_THREADS = 128;
+constexpr int PK_WARPS = PK_THREADS / 32;
+constexpr int PK_MIN_BLOCKS = 5;     // register budget: 65536 / (5 * 128) = 102
+constexpr int PK_STACK = 96;         // reference STACK_SIZE is 64 (kernel_config.h:13)
+constexpr int PK_QD = 8;             // FIFO depth per lane
+constexpr int PK_BATCH = 8;          // leaves fetched together
+
+template <int MODE, int M4>
+struct PkWarp {
+    static constexpr bool NEED_Q = (MODE == MODE_CUMULATIVE || MODE == MODE_FILL);
+    static constexpr bool NEED_I = (MODE == MODE_FILL);
+    float4 prims[M4];                          // staged leaf {x,y,z,h*h} or {c-o, h*h}
+    float4 rays[64];                           // ray r: {dx,dy,dz,ox} {oy,oz,len,-}
+    float4 raw[PK_BATCH * M4];                 // cp.async landing zone
+    int2 stack[PK_STACK];                      // {node or leaf index, lane mask}
+    float ir[NEED_Q ? M4 : 4];                 // 1/h of the staged spheres
+    float2 q[NEED_Q ? PK_QD * 32 : 2];         // FIFO {b2, 1/h}, [slot][lane]
+    int idx[NEED_I ? M4 : 4];                  // primitive index of the staged spheres
+    float2 q2[NEED_I ? PK_QD * 32 : 2];        // FIFO {distance, index bits}
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void prefetch_l1(const void* p)
+{
+    asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+}
+
+// cuda/functors/trace.cuh:183-186 + generic/interpolate.h:15-38 with 1/h precomputed (the
+// same IEEE quotient the reference forms per hit).
+__device__ __forceinline__ float pk_integral(float b2, float ir, const double* table)
+{
+    float x = __fmul_rn(__fmul_rn(__fsqrt_rn(b2), ir), 50.0f);
+    int i = __float2int_rz(x);
+    if (i >= N_TABLE - 1) { x = (float)(N_TABLE - 1); i = N_TABLE - 2; }
+    i = max(i, 0);
+    const double y0 = table[i], y1 = table[i + 1];
+    const double t = __dsub_rn((double)x, (double)i);
+    const double y = __fma_rn(t, __dsub_rn(y1, y0), y0);
+    return __fmul_rn((float)y, __fmul_rn(ir, ir));
+}
+
+// Evaluate a lane's FIFO in order.  Real calls (not inlined): the kernel has ~10 call sites
+// and each copy is ~150 SASS instructions.
+__device__ __noinline__ float pk_flush_cum(const float2* q, int qn, int lane, const double* table, float cum)
+{
+    __syncwarp();       // entries may have been written by other lanes (transposed leaves)
+    const int nmax = __reduce_max_sync(0xffffffffu, qn);
+    for (int j = 0; j < nmax; ++j) {
+        if (j < qn) {
+            const float2 e = q[j * 32 + lane];
+            cum = __fadd_rn(cum, pk_integral(e.x, e.y, table));
+        }
+    }
+    __syncwarp();
+    return cum;
+}
+
+__device__ __noinline__ int pk_flush_fill(const float2* q, const float2* q2, int qn, int lane,
+                                          const double* table, int cursor, int* hit_idx,
+                                          float* hit_integral, float* hit_dist)
+{
+    __syncwarp();
+    const int nmax = __reduce_max_sync(0xffffffffu, qn);
+    for (int j = 0; j < nmax; ++j) {
+        if (j < qn) {
+            const float2 e = q[j * 32 + lane];
+            const float2 e2 = q2[j * 32 + lane];
+            hit_idx[cursor] = __float_as_int(e2.y);
+            hit_integral[cursor] = pk_integral(e.x, e.y, table);
+            hit_dist[cursor] = e2.x;
+            ++cursor;
+        }
+    }
+    __syncwarp();
+    return cursor;
+}
+
+// Everything a packet accumulates per lane, plus where hit lists go.
+struct PkAcc {
+    int count; float cum; int cursor; int qn;
+    int* hit_idx; float* hit_integral; float* hit_dist;
+};
+
+template <int MODE, int M4>
+__device__ __forceinline__ void pk_flush(PkWarp<MODE, M4>& W, PkAcc& A, int lane, const double* table)
+{
+    if (MODE == MODE_CUMULATIVE) A.cum = pk_flush_cum(W.q, A.qn, lane, table, A.cum);
+    if (MODE == MODE_FILL)
+        A.cursor = pk_flush_fill(W.q, W.q2, A.qn, lane, table, A.cursor, A.hit_idx, A.hit_integral, A.hit_dist);
+    A.qn = 0;
+}
+
+// ---- conservative bound of a whole packet --------------------------------------------
+// Every point of every ray lies within r0 + max(0, t - t0min) * tan(theta) of the axis line
+// (oc, a), t being the axial coordinate.  A sphere farther than that (+ h + slack) from the
+// axis, or entirely behind every origin, cannot be hit by any ray of the packet.
+struct PacketBound {
+    float ax, ay, az;       // axis direction (unit)
+    float ocx, ocy, ocz;    // a point on the axis (lane 0's origin)
+    float r0, tan_t, t0min;
+    bool enabled;
+};
+
+__device__ __forceinline__ float warp_max(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_min(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ PacketBound packet_bound(const grace_b200_ray& ray)
+{
+    PacketBound B;
+    const float sx = warp_sum(ray.dx), sy = warp_sum(ray.dy), sz = warp_sum(ray.dz);
+    const float n2 = sx * sx + sy * sy + sz * sz;
+    const float inv = rsqrtf(fmaxf(n2, 1e-30f));
+    B.ax = sx * inv; B.ay = sy * inv; B.az = sz * inv;
+    B.ocx = __shfl_sync(0xffffffffu, ray.ox, 0);
+    B.ocy = __shfl_sync(0xffffffffu, ray.oy, 0);
+    B.ocz = __shfl_sync(0xffffffffu, ray.oz, 0);
+    const float wx = ray.ox - B.ocx, wy = ray.oy - B.ocy, wz = ray.oz - B.ocz;
+    const float t0 = wx * B.ax + wy * B.ay + wz * B.az;
+    const float qx = wx - t0 * B.ax, qy = wy - t0 * B.ay, qz = wz - t0 * B.az;
+    const float perp = sqrtf(qx * qx + qy * qy + qz * qz);
+    const float cosl = ray.dx * B.ax + ray.dy * B.ay + ray.dz * B.az;
+    const float cmin = warp_min(cosl);
+    B.r0 = warp_max(perp) * 1.0001f;
+    B.t0min = warp_min(t0);
+    // NaNs (degenerate rays) make the comparisons false -> culling disabled
+    B.enabled = (n2 > 1.0f) && (cmin > 0.5f) && (B.r0 < 1e30f);
+    const float c = fminf(cmin, 1.0f);
+    B.tan_t = sqrtf(fmaxf(1.0f - c * c, 0.0f)) / c * 1.001f + 1e-6f;
+    return B;
+}
+
+__device__ __forceinline__ bool packet_may_hit(const PacketBound& B, const float4 s)
+{
+    const float px = s.x - B.ocx, py = s.y - B.ocy, pz = s.z - B.ocz;
+    const float t = px * B.ax + py * B.ay + pz * B.az;
+    const float qx = px - t * B.ax, qy = py - t * B.ay, qz = pz - t * B.az;
+    const float d2 = qx * qx + qy * qy + qz * qz;
+    const float scale = fabsf(px) + fabsf(py) + fabsf(pz) + B.r0 + s.w;
+    const float slack = 2e-5f * scale;
+    const float R = B.r0 + fmaxf(0.0f, t + s.w - B.t0min) * B.tan_t + s.w + slack;
+    const bool outside = d2 > R * R;
+    const bool behind = (t + s.w + slack) < B.t0min;
+    return !(outside || behind);
+}
+
+// One sphere against one ray: generic/intersect.h:16-48 in the SASS-verified contraction.
+// COMMON: the staged xyz already hold c - o.  s.w holds h*h.
+template <bool COMMON>
+__device__ __forceinline__ bool pk_test(const float4 s, float ox, float oy, float oz,
+                                        float dx, float dy, float dz, float len,
+                                        float& b2, float& dot)
+{
+    const float px = COMMON ? s.x : __fsub_rn(s.x, ox);
+    const float py = COMMON ? s.y : __fsub_rn(s.y, oy);
+    const float pz = COMMON ? s.z : __fsub_rn(s.z, oz);
+    dot = __fmul_rn(py, dy);
+    dot = __fmaf_rn(px, dx, dot);
+    dot = __fmaf_rn(pz, dz, dot);
+    const float bx = __fmaf_rn(-dx, dot, px);
+    const float by = __fmaf_rn(-dy, dot, py);
+    const float bz = __fmaf_rn(-dz, dot, pz);
+    b2 = __fmul_rn(by, by);
+    b2 = __fmaf_rn(bx, bx, b2);
+    b2 = __fmaf_rn(bz, bz, b2);
+    return !(b2 >= s.w) && !(dot < 0.0f) && !(dot >= len);
+}
+
+// Dense leaf: every lane tests every staged sphere against its own ray.
+template <int MODE, int M4, bool COMMON>
+__device__ __forceinline__ void pk_leaf_dense(PkWarp<MODE, M4>& W, int n_kept, const grace_b200_ray& ray,
+                                              int lane, bool lane_on, PkAcc& A, const double* table)
+{
+#pragma unroll 2
+    for (int i = 0; i < n_kept; ++i) {
+        const float4 s = W.prims[i];
+        float b2, dot;
+        const bool hit = pk_test<COMMON>(s, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, ray.length, b2, dot) && lane_on;
+        if (MODE == MODE_COUNT) {
+            A.count += (int)hit;
+        } else {
+            if (hit) {
+                W.q[A.qn * 32 + lane] = make_float2(b2, W.ir[i]);
+                if (MODE == MODE_FILL) W.q2[A.qn * 32 + lane] = make_float2(dot, __int_as_float(W.idx[i]));
+                ++A.qn;
+            }
+            if (__any_sync(0xffffffffu, A.qn == PK_QD)) pk_flush<MODE, M4>(W, A, lane, table);
+        }
+    }
+}
+
+// Sparse leaf: lane j holds staged sphere j; the rays in `mask` are visited one by one
+// (shared-memory broadcast) and hits go straight into the owning ray's FIFO, in ascending
+// sphere order.
+template <int MODE, int M4, bool COMMON>
+__device__ __forceinline__ void pk_leaf_sparse(PkWarp<MODE, M4>& W, unsigned mask, int n_kept, int lane,
+                                               unsigned lt, PkAcc& A, const double* table)
+{
+    for (int base = 0; base < n_kept; base += 32) {
+        const int j = base + lane;
+        const bool have = j < n_kept;
+        const float4 s = have ? W.prims[j] : make_float4(0.f, 0.f, 0.f, -1.f);
+        float ir = 0.f;
+        int pidx = 0;
+        if (MODE != MODE_COUNT && have) ir = W.ir[j];
+        if (MODE == MODE_FILL && have) pidx = W.idx[j];
+        unsigned m = mask;
+        while (m) {
+            const int r = __ffs(m) - 1;
+            m &= m - 1;
+            const float4 ra = W.rays[2 * r];
+            const float4 rb = W.rays[2 * r + 1];
+            float b2, dot;
+            const bool hit = pk_test<COMMON>(s, ra.w, rb.x, rb.y, ra.x, ra.y, ra.z, rb.z, b2, dot) && have;
+            const unsigned hm = __ballot_sync(0xffffffffu, hit);
+            if (hm == 0u) continue;
+            const int nh = __popc(hm);
+            if (MODE == MODE_COUNT) {
+                if (lane == r) A.count += nh;
+            } else {
+                const int rank = __popc(hm & lt);
+                int qn_r = __shfl_sync(0xffffffffu, A.qn, r);
+                int done = 0;
+                while (done < nh) {
+                    if (qn_r == PK_QD) { pk_flush<MODE, M4>(W, A, lane, table); qn_r = 0; }
+                    const int take = min(PK_QD - qn_r, nh - done);
+                    if (hit && rank >= done && rank < done + take) {
+                        W.q[(qn_r + rank - done) * 32 + r] = make_float2(b2, ir);
+                        if (MODE == MODE_FILL) W.q2[(qn_r + rank - done) * 32 + r] = make_float2(dot, __int_as_float(pidx));
+                    }
+                    if (lane == r) A.qn += take;
+                    qn_r += take;
+                    done += take;
+                }
+            }
+        }
+    }
+    if (MODE != MODE_COUNT) {
+        if (__any_sync(0xffffffffu, A.qn == PK_QD)) pk_flush<MODE, M4>(W, A, lane, table);
+    }
+}
+
+// Suspended traversals (load balancing): a unit of work that has run `budget` steps saves its
+// state in a record and is resumed in the next launch as up to 32/child_width tasks, each
+// owning the rays of one aligned block of child_width lanes.  Every ray keeps accumulating in
+// the same (ascending primitive) order, so results do not depend on whether or where a
+// traversal was split.
+constexpr int PK_REC_WORDS = 8 + 2 * PK_STACK + 3 * 32;   // header | stack | cum, count, cursor
+struct PkTasks {
+    const int2* tasks_in;     // {record, ray subset}; NULL in round 0 (units are packets)
+    const int* n_tasks_in;
+    int2* tasks_out;          // NULL in the last round (run to completion)
+    int* n_tasks_out;
+    int* records;
+    int* n_records;
+    int tasks_cap, records_cap;
+    int budget;               // steps (inner nodes + leaves) before a unit may be suspended
+    int child_width;          // lanes per child task
+};
+
+// Claim `n` consecutive slots of a bounded pool; -1 if they do not fit.
+__device__ __forceinline__ int pk_reserve(int* counter, int n, int cap)
+{
+    int cur = *(volatile int*)counter;
+    for (;;) {
+        if (cur + n > cap) return -1;
+        const int seen = atomicCAS(counter, cur, cur + n);
+        if (seen == cur) return cur;
+        cur = seen;
+    }
+}
+
+struct PkArgs {
+    const grace_b200_ray* rays; int n_packets;
+    const float4* spheres; const int4* nodes; const int4* leaves; int n_nodes; const int* root_ptr;
+    int* out_counts; float* out_cum; const int* offsets;
+    int* hit_idx; float* hit_integral; float* hit_dist;
+    int* unit_counter; int* err_flag; unsigned long long* prof;
+};
+
+template <int MODE, int M4>
+__global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS)
+trace_packet_kernel(const PkArgs P, const PkTasks T)
+{
+    using Warp = PkWarp<MODE, M4>;
+    constexpr bool NEED_Q = Warp::NEED_Q;
+    extern __shared__ __align__(16) unsigned char pk_smem[];
+    double* s_table = (double*)pk_smem;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Warp& W = *((Warp*)(pk_smem + 52 * sizeof(double)) + warp);
+    if (NEED_Q) {
+        for (int i = threadIdx.x; i < N_TABLE; i += PK_THREADS) s_table[i] = c_kernel_table[i];
+        __syncthreads();
+    }
+    const float4* __restrict__ spheres = P.spheres;
+    const int4* __restrict__ nodes = P.nodes;
+    const int4* __restrict__ leaves = P.leaves;
+    const int n_nodes = P.n_nodes;
+    const int root = __ldg(P.root_ptr);
+    const unsigned lt = gb_lanemask_lt();
+    const int n_units = T.tasks_in ? min(__ldg(T.n_tasks_in), T.tasks_cap) : P.n_packets;
+
+    for (;;) {
+        int unit = 0;
+        if (lane == 0) unit = atomicAdd(P.unit_counter, 1);
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        if (unit >= n_units) break;
+        int packet = unit;
+        unsigned subset = 0xffffffffu;
+        const int* rec = nullptr;
+        if (T.tasks_in) {
+            const int2 t = T.tasks_in[unit];
+            if (t.x < 0) continue;            // slot claimed but never filled (pool was full)
+            rec = T.records + (size_t)t.x * PK_REC_WORDS;
+            packet = rec[0];
+            subset = (unsigned)t.y;
+        }
+        const bool lane_on = (subset >> lane) & 1u;
+        const int ray_index = packet * 32 + lane;
+        const grace_b200_ray ray = P.rays[ray_index];
+        __syncwarp();
+        W.rays[2 * lane] = make_float4(ray.dx, ray.dy, ray.dz, ray.ox);
+        W.rays[2 * lane + 1] = make_float4(ray.oy, ray.oz, ray.length, 0.f);
+        const float ix = __fdiv_rn(1.0f, ray.dx), iy = __fdiv_rn(1.0f, ray.dy),
+                    iz = __fdiv_rn(1.0f, ray.dz);
+        const float pad = 64.0f * 5.9604645e-8f *
+                          (fabsf(ray.ox) + fabsf(ray.oy) + fabsf(ray.oz) + fabsf(ray.length));
+        // t_bottom = fma(b, inv, cb), t_top = fma(t, inv, ct) with the box grown by pad
+        const float cbx = -(ray.ox + pad) * ix, ctx = -(ray.ox - pad) * ix;
+        const float cby = -(ray.oy + pad) * iy, cty = -(ray.oy - pad) * iy;
+        const float cbz = -(ray.oz + pad) * iz, ctz = -(ray.oz - pad) * iz;
+        const PacketBound B = packet_bound(ray);
+        // all 32 rays share one origin?  (comparisons AFTER the shuffles in packet_bound:
+        // every lane must execute every shuffle)
+        const bool common = __all_sync(0xffffffffu, (ray.ox == B.ocx) & (ray.oy == B.ocy) & (ray.oz == B.ocz));
+        PkAcc A;
+        A.count = 0; A.cum = 0.0f; A.cursor = 0; A.qn = 0;
+        A.hit_idx = P.hit_idx; A.hit_integral = P.hit_integral; A.hit_dist = P.hit_dist;
+        int sp = 0;
+        int top = root;
+        unsigned top_mask = 0xffffffffu;
+        if (rec) {      // resume a suspended traversal for the rays in `subset`
+            sp = rec[2]; top = rec[3]; top_mask = (unsigned)rec[4] & subset;
+            for (int i = lane; i < sp; i += 32) W.stack[i] = ((const int2*)(rec + 8))[i];
+            A.cum = __int_as_float(rec[8 + 2 * PK_STACK + lane]);
+            A.count = rec[8 + 2 * PK_STACK + 32 + lane];
+            A.cursor = rec[8 + 2 * PK_STACK + 64 + lane];
+        } else if (MODE == MODE_FILL) {
+            A.cursor = P.offsets[ray_index];
+        }
+        __syncwarp();
+
+        unsigned long long pf_nodes = 0, pf_leaves = 0, pf_staged = 0, pf_kept = 0;
+        const long long pf_t0 = P.prof ? clock64() : 0;
+        const int guard0 = 2 * n_nodes + 8;   // a depth-first walk enters each node at most once
+        int guard = guard0;
+        bool suspended = false;
+        for (;;) {
+            // ---- suspend an over-budget traversal and hand its rays to several tasks ----
+            if (T.tasks_out && guard0 - guard >= T.budget && top >= 0) {
+                const unsigned bmask0 = T.child_width >= 32 ? 0xffffffffu : ((1u << T.child_width) - 1u);
+                unsigned blocks = 0;          // bit b: some ray of lane block b belongs to this unit
+                for (int b = 0; b * T.child_width < 32; ++b)
+                    if (subset & (bmask0 << (b * T.child_width))) blocks |= 1u << b;
+                const int nchild = __popc(blocks);
+                int rslot = -1, tslot = -1;
+                if (nchild > 1 && lane == 0) {
+                    // Reserve with compare-and-swap: a counter must never be visible above its
+                    // final value (an add-then-undo would let another warp claim slots past it).
+                    tslot = pk_reserve(T.n_tasks_out, nchild, T.tasks_cap);
+                    if (tslot >= 0) {
+                        rslot = pk_reserve(T.n_records, 1, T.records_cap);
+                        if (rslot < 0) {       // no record: publish nothing in the claimed task slots
+                            for (int c = 0; c < nchild; ++c) T.tasks_out[tslot + c] = make_int2(-1, 0);
+                        }
+                    }
+                }
+                rslot = __shfl_sync(0xffffffffu, rslot, 0);
+                tslot = __shfl_sync(0xffffffffu, tslot, 0);
+                if (rslot >= 0) {
+                    if (NEED_Q) pk_flush<MODE, M4>(W, A, lane, s_table);
+                    int* r = T.records + (size_t)rslot * PK_REC_WORDS;
+                    if (lane == 0) { r[0] = packet; r[1] = (int)subset; r[2] = sp; r[3] = top; r[4] = (int)top_mask; }
+                    for (int i = lane; i < sp; i += 32) ((int2*)(r + 8))[i] = W.stack[i];
+                    r[8 + 2 * PK_STACK + lane] = __float_as_int(A.cum);
+                    r[8 + 2 * PK_STACK + 32 + lane] = A.count;
+                    r[8 + 2 * PK_STACK + 64 + lane] = A.cursor;
+                    if (lane < nchild) {      // lane c publishes the c-th non-empty block
+                        unsigned bb = blocks;
+                        for (int c = 0; c < lane; ++c) bb &= bb - 1;
+                        const int b = __ffs(bb) - 1;
+                        T.tasks_out[tslot + lane] = make_int2(rslot, (int)(subset & (bmask0 << (b * T.child_width))));
+                    }
+                    suspended = true;
+                    break;
+                }
+            }
+            // ---- phase A: walk inner nodes until PK_BATCH leaves are collected ----
+            int nb = 0;
+            int b_leaf = 0;               // lane b holds batch entry b
+            unsigned b_mask = 0;
+            while (top >= 0 && nb < PK_BATCH) {
+                if (top_mask == 0u) {     // nothing below this entry concerns this unit's rays
+                    if (sp > 0) { const int2 e = W.stack[--sp]; top = e.x; top_mask = (unsigned)e.y & subset; }
+                    else top = -1;
+                    continue;
+                }
+                if (--guard < 0) { if (lane == 0) atomicMax(P.err_flag, 2); top = -1; break; }
+                if (top < n_nodes) {
+                    if (P.prof) ++pf_nodes;
+                    const int4* np = nodes + 4 * (size_t)top;
+                    const int4 n0 = __ldg(np + 0);
+                    const int4 n1 = __ldg(np + 1);
+                    const int4 n2 = __ldg(np + 2);
+                    const int4 n3 = __ldg(np + 3);
+                    bool hitL, hitR;
+                    {
+                        const float a0 = fmaf(__int_as_float(n1.x), ix, cbx), a1 = fmaf(__int_as_float(n1.y), ix, ctx);
+                        const float b0 = fmaf(__int_as_float(n1.z), iy, cby), b1 = fmaf(__int_as_float(n1.w), iy, cty);
+                        const float c0 = fmaf(__int_as_float(n3.x), iz, cbz), c1 = fmaf(__int_as_float(n3.y), iz, ctz);
+                        const float tmin = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), 0.0f));
+                        const float tmax = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), ray.length));
+                        hitL = !(tmax < tmin);
+                    }
+                    {
+                        const float a0 = fmaf(__int_as_float(n2.x), ix, cbx), a1 = fmaf(__int_as_float(n2.y), ix, ctx);
+                        const float b0 = fmaf(__int_as_float(n2.z), iy, cby), b1 = fmaf(__int_as_float(n2.w), iy, cty);
+                        const float c0 = fmaf(__int_as_float(n3.z), iz, cbz), c1 = fmaf(__int_as_float(n3.w), iz, ctz);
+                        const float tmin = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), 0.0f));
+                        const float tmax = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), ray.length));
+                        hitR = !(tmax < tmin);
+                    }
+                    // a lane that missed an ancestor's box cannot hit anything below it
+                    const unsigned mL = __ballot_sync(0xffffffffu, hitL) & top_mask;
+                    const unsigned mR = __ballot_sync(0xffffffffu, hitR) & top_mask;
+                    if (mL && mR) {
+                        if (sp >= PK_STACK) { if (lane == 0) atomicMax(P.err_flag, 1); top = -1; sp = 0; continue; }
+                        W.stack[sp++] = make_int2(n0.y, (int)mR);
+                        // the right child is needed after the whole left subtree: warm its line
+                        if (lane == 0) prefetch_l1(n0.y < n_nodes ? (const void*)(nodes + 4 * (size_t)n0.y)
+                                                                  : (const void*)(leaves + (n0.y - n_nodes)));
+                        top = n0.x; top_mask = mL;
+                    } else if (mL) {
+                        top = n0.x; top_mask = mL;
+                    } else if (mR) {
+                        top = n0.y; top_mask = mR;
+                    } else {
+                        if (sp > 0) { const int2 e = W.stack[--sp]; top = e.x; top_mask = (unsigned)e.y & subset; }
+                        else top = -1;
+                    }
+                } else {
+                    if (lane == nb) { b_leaf = top - n_nodes; b_mask = top_mask; }
+                    ++nb;
+                    if (sp > 0) { const int2 e = W.stack[--sp]; top = e.x; top_mask = (unsigned)e.y & subset; }
+                    else top = -1;
+                }
+            }
+            if (nb == 0) break;
+            // ---- phase B: all leaf records in one round trip, then all spheres in one ----
+            int2 lf = make_int2(0, 0);
+            if (lane < nb) lf = __ldg((const int2*)(leaves + b_leaf));
+            for (int slot = 0; slot < nb; ++slot) {
+                const int first = __shfl_sync(0xffffffffu, lf.x, slot);
+                const int cnt = min(__shfl_sync(0xffffffffu, lf.y, slot), M4);
+                for (int i = lane; i < cnt; i += 32)
+                    cp_async16(&W.raw[slot * M4 + i], spheres + first + i);
+            }
+            cp_async_wait_all();
+            __syncwarp();
+            // ---- phase C: cull, compact and test leaf by leaf (ascending order) ----
+            for (int slot = 0; slot < nb; ++slot) {
+                const int first = __shfl_sync(0xffffffffu, lf.x, slot);
+                const int cnt = min(__shfl_sync(0xffffffffu, lf.y, slot), M4);
+                const unsigned leaf_mask = __shfl_sync(0xffffffffu, b_mask, slot);
+                int n_kept = 0;
+                for (int base = 0; base < cnt; base += 32) {
+                    const int i = base + lane;
+                    bool keep = false;
+                    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (i < cnt) {
+                        s = W.raw[slot * M4 + i];
+                        keep = !B.enabled || packet_may_hit(B, s);
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, keep);
+                    if (keep) {
+                        const int dst = n_kept + __popc(m & lt);
+                        if (NEED_Q) W.ir[dst] = __fdiv_rn(1.0f, s.w);
+                        if (MODE == MODE_FILL) W.idx[dst] = first + i;
+                        s.w = __fmul_rn(s.w, s.w);
+                        if (common) {
+                            s.x = __fsub_rn(s.x, ray.ox); s.y = __fsub_rn(s.y, ray.oy); s.z = __fsub_rn(s.z, ray.oz);
+                        }
+                        W.prims[dst] = s;
+                    }
+                    n_kept += __popc(m);
+                }
+                __syncwarp();
+                if (P.prof) { ++pf_leaves; pf_staged += cnt; pf_kept += n_kept; }
+                const int k_active = __popc(leaf_mask);
+                if (3 * k_active < 2 * n_kept) {
+                    if (common) pk_leaf_sparse<MODE, M4, true>(W, leaf_mask, n_kept, lane, lt, A, s_table);
+                    else pk_leaf_sparse<MODE, M4, false>(W, leaf_mask, n_kept, lane, lt, A, s_table);
+                } else {
+                    if (common) pk_leaf_dense<MODE, M4, true>(W, n_kept, ray, lane, lane_on, A, s_table);
+                    else pk_leaf_dense<MODE, M4, false>(W, n_kept, ray, lane, lane_on, A, s_table);
+                }
+                __syncwarp();
+            }
+        }
+        if (suspended) continue;
+        if (NEED_Q) pk_flush<MODE, M4>(W, A, lane, s_table);
+        if (MODE == MODE_COUNT && lane_on) P.out_counts[ray_index] = A.count;
+        if (MODE == MODE_CUMULATIVE && lane_on) P.out_cum[ray_index] = A.cum;
+        if (P.prof && lane == 0) {
+            atomicAdd(P.prof + 0, pf_nodes); atomicAdd(P.prof + 1, pf_leaves);
+            atomicAdd(P.prof + 2, pf_staged); atomicAdd(P.prof + 3, pf_kept);
+            unsigned long long* pp = P.prof + 4 + 4 * (size_t)packet;   // per-packet record
+            pp[0] = (unsigned long long)(clock64() - pf_t0); pp[1] = pf_nodes; pp[2] = pf_leaves; pp[3] = pf_kept;
+        }
+    }
+}
+
+template <int MODE, int M4>
+constexpr size_t packet_smem_bytes()
+{
+    return 52 * sizeof(double) + PK_WARPS * sizeof(PkWarp<MODE, M4>);
+}

@@ -151,15 +151,28 @@ typedef struct {
     int max_per_leaf;
 } grace_b200_tree;
 
-/* Traversal schedule.  PER_RAY (default): every lane walks the tree for its own ray with a
- * conservatively padded slab test; the hit set is exactly the brute-force set.  PACKET:
- * the reference's schedule (cuda/kernels/bintree_trace.cuh:119-193: 32 consecutive rays
- * share one stack, a node is entered if ANY lane hits it), kept for A/B measurements and
- * for the traversal counters.  Both give identical results wherever the reference passes
- * its own brute-force test (tests/tree_traversal/tree_traversal.cu:84-121). */
-#define GRACE_B200_TRACE_PER_RAY 0
-#define GRACE_B200_TRACE_PACKET  1
+/* Traversal schedule (all three return identical results wherever the reference passes
+ * its own brute-force test, tests/tree_traversal/tree_traversal.cu:84-121).
+ *  PACKET (default): 32 consecutive rays share one traversal as in the reference
+ *     (cuda/kernels/bintree_trace.cuh:119-193), with a conservatively padded slab test,
+ *     staged leaves and deferred on-hit work; the hit set is exactly the brute-force set.
+ *  PER_RAY: every lane walks the tree for its own ray (padded slab test).
+ *  PACKET_REF: the reference's schedule and slab arithmetic bit for bit; defines the
+ *     traversal counters of grace_b200_trace_stats_f4. */
+#define GRACE_B200_TRACE_PER_RAY    0
+#define GRACE_B200_TRACE_PACKET     1
+#define GRACE_B200_TRACE_PACKET_REF 2
 int grace_b200_set_trace_mode(grace_b200_ctx* ctx, int mode);
+/* Load balancing of the PACKET schedule: a packet whose traversal exceeds `steps` inner-node
+ * + leaf visits is suspended and resumed as several tasks over disjoint subsets of its rays
+ * (results are unaffected: each ray accumulates in the same order).  0 disables splitting;
+ * the default is 2048. */
+int grace_b200_set_trace_budget(grace_b200_ctx* ctx, int steps);
+/* Device-side error flag of the last trace launch: 0 = none, 1 = traversal stack overflow
+ * (the reference asserts on this only under GRACE_DEBUG, bintree_trace.cuh:162-164),
+ * 2 = traversal did not terminate within 2*n_nodes steps (malformed tree).
+ * Synchronises the stream. */
+int grace_b200_device_error(grace_b200_ctx* ctx, int* h_flag, void* stream);
 
 /* All trace calls return GRACE_B200_EINVAL unless n_rays % 32 == 0
  * (bintree_trace.cuh:231-238): a packet is 32 consecutive rays. */
@@ -199,6 +212,16 @@ int grace_b200_trace_hits_fill_f4(grace_b200_ctx* ctx, const grace_b200_ray* d_r
 int grace_b200_trace_stats_f4(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, size_t n_rays,
                               const float* d_spheres4, size_t n, const grace_b200_tree* tree,
                               long long* h_stats4, void* stream);
+
+/* Diagnostic: work counters of the production packet kernel (hit-count mode):
+ * h_prof4 = {inner-node steps, leaf visits, primitives in visited leaves, primitives kept
+ * after the packet-bound cull}; with h_per_packet != 0 the buffer must hold
+ * 4 + 4*(n_rays/32) values and also receives {cycles, node steps, leaf visits, kept} per
+ * packet.  Synchronises the stream. */
+int grace_b200_trace_packet_profile_f4(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, size_t n_rays,
+                                       const float* d_spheres4, size_t n, const grace_b200_tree* tree,
+                                       int* d_hit_counts, long long* h_prof4, int h_per_packet,
+                                       void* stream);
 
 /* Diagnostic: per-ray cost of the per-ray traversal (sphere tests and inner-node steps). */
 int grace_b200_trace_ray_cost_f4(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, size_t n_rays,

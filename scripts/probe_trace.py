@@ -21,17 +21,31 @@ def timeit(fn, reps=3):
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / reps
 
-for mode in ("ray", "packet"):
+for mode in ("ray", "packet_ref", "packet"):
     gb.set_trace_mode(mode)
     print(mode, "hitcounts ms", timeit(lambda: gb.trace_hitcounts_sph(rays, s, tree, counts)),
           "cumulative ms", timeit(lambda: gb.trace_cumulative_sph(rays, s, tree, out)))
-gb.set_trace_mode("ray")
 h = counts.cpu().numpy().astype(np.int64)
 print("hits: mean %.0f max %d p50 %d p99 %d p99.9 %d p99.99 %d" % (h.mean(), h.max(), *np.percentile(h, [50, 99, 99.9, 99.99])))
 hs = s[:, 3].cpu().numpy()
 print("h: min %.3g p1 %.3g p50 %.3g p99 %.3g max %.3g" % (hs.min(), *np.percentile(hs, [1, 50, 99]), hs.max()))
 lv = tree.leaves.cpu().numpy()
 print("leaves", len(lv), "mean count", lv[:, 1].mean())
+for bud in (0, 1024, 2048, 4096, 8192):
+    gb.set_trace_budget(bud)
+    print("budget", bud, "hitcounts ms", timeit(lambda: gb.trace_hitcounts_sph(rays, s, tree, counts)),
+          "cumulative ms", timeit(lambda: gb.trace_cumulative_sph(rays, s, tree, out)), "err", gb.device_error())
+gb.set_trace_budget(2048)
+pp = gb.trace_packet_profile_sph(rays, s, tree)
+per = pp.pop("per_packet")
+print("packet profile", pp)
+cyc = per[:, 0]
+print("per-packet cycles: mean %.3g max %.3g p99 %.3g ; sum/1e9 %.3f" % (cyc.mean(), cyc.max(), np.percentile(cyc, 99), cyc.sum() / 1e9))
+w = np.argsort(-cyc)[:8]
+print("heaviest packets", w, "\n cycles", cyc[w], "\n phaseA(nodes)", per[w, 1], "\n phaseB(loads)", per[w, 2], "\n phaseC(tests)", per[w, 3])
+print("all packets: A %.3g B %.3g C %.3g (sum cycles /1e9)" % (per[:, 1].sum() / 1e9, per[:, 2].sum() / 1e9, per[:, 3].sum() / 1e9))
+print("ref packet stats", gb.trace_stats_sph(rays, s, tree))
+gb.set_trace_mode("packet")
 tests, steps = gb.trace_ray_cost_sph(rays, s, tree)
 t = tests.cpu().numpy().astype(np.int64); st_ = steps.cpu().numpy().astype(np.int64)
 print("tests/ray: mean %.0f max %d p50 %d p99 %d p99.9 %d p99.99 %d" % (t.mean(), t.max(), *np.percentile(t, [50, 99, 99.9, 99.99])))

@@ -188,12 +188,12 @@ def test_tree_tiny_and_errors(gb, orc):
 
 
 # ----------------------------------------------------------------------------- trace
-@pytest.fixture(params=["ray", "packet"], autouse=True)
+@pytest.fixture(params=["packet", "ray", "packet_ref"], autouse=True)
 def trace_mode(request, gb):
     """Every test below runs under both traversal schedules."""
     gb.set_trace_mode(request.param)
     yield request.param
-    gb.set_trace_mode("ray")
+    gb.set_trace_mode("packet")
 
 
 @pytest.fixture(scope="module")
@@ -264,6 +264,35 @@ def test_hit_lists_and_sort(gb, orc, scene):
     assert np.array_equal(host(dist).view(np.uint32), sd.view(np.uint32))
     assert np.array_equal(host(idx), si)
     assert np.array_equal(host(integ).view(np.uint32), sg.view(np.uint32))
+
+
+@pytest.mark.parametrize("budget", [8, 100, 1000])
+def test_packet_splitting_is_exact(gb, orc, scene, budget, trace_mode):
+    """Over-budget packets are suspended and resumed as ray-subset tasks; with a tiny
+    budget nearly every packet goes through all four rounds.  Results must not change."""
+    if trace_mode != "packet":
+        pytest.skip("splitting exists only in the production packet schedule")
+    d_s, tree, hs, htree, rays = scene
+    gb.set_trace_budget(budget)
+    try:
+        d_rays = dev(rays)
+        cnt = torch.empty(len(rays), dtype=torch.int32, device="cuda")
+        cum = torch.empty(len(rays), dtype=torch.float32, device="cuda")
+        gb.trace_hitcounts_sph(d_rays, d_s, tree, cnt)
+        gb.trace_cumulative_sph(d_rays, d_s, tree, cum)
+        assert gb.device_error() == 0
+        assert np.array_equal(host(cnt), orc.trace_hitcounts(rays, hs, htree))
+        ref = orc.trace_cumulative(rays, hs, htree)
+        assert np.array_equal(host(cum).view(np.uint32), ref.view(np.uint32))
+        sub = rays[:1024]
+        off = torch.empty(len(sub), dtype=torch.int32, device="cuda")
+        idx, integ, dist = gb.trace_sph(dev(sub), d_s, tree, off)
+        roff, ridx, rinteg, rdist = orc.trace_hits(sub, hs, htree)
+        assert np.array_equal(host(off), roff) and np.array_equal(host(idx), ridx)
+        assert np.array_equal(host(integ).view(np.uint32), rinteg.view(np.uint32))
+        assert np.array_equal(host(dist).view(np.uint32), rdist.view(np.uint32))
+    finally:
+        gb.set_trace_budget(2048)
 
 
 def test_hit_lists_with_sentinels(gb, orc, scene):
