@@ -70,7 +70,7 @@ __device__ __forceinline__ void prefetch_l1(const void* p)
 
 // cuda/functors/trace.cuh:183-186 + generic/interpolate.h:15-38 with 1/h precomputed (the
 // same IEEE quotient the reference forms per hit).
-__device__ __forceinline__ float pk_integral(float b2, float ir, const double* table)
+__device__ __forceinline__ float pk_lerp(float b2, float ir, const double* table)
 {
     float x = __fmul_rn(__fmul_rn(__fsqrt_rn(b2), ir), 50.0f);
     int i = __float2int_rz(x);
@@ -78,8 +78,12 @@ __device__ __forceinline__ float pk_integral(float b2, float ir, const double* t
     i = max(i, 0);
     const double y0 = table[i], y1 = table[i + 1];
     const double t = __dsub_rn((double)x, (double)i);
-    const double y = __fma_rn(t, __dsub_rn(y1, y0), y0);
-    return __fmul_rn((float)y, __fmul_rn(ir, ir));
+    return (float)__fma_rn(t, __dsub_rn(y1, y0), y0);
+}
+// per-hit value as stored (OnHit_sphere_individual): one FMUL
+__device__ __forceinline__ float pk_integral(float b2, float ir, const double* table)
+{
+    return __fmul_rn(pk_lerp(b2, ir, table), __fmul_rn(ir, ir));
 }
 
 // Evaluate a lane's FIFO in order.  Real calls (not inlined): the kernel has ~10 call sites
@@ -91,7 +95,8 @@ __device__ __noinline__ float pk_flush_cum(const float2* q, int qn, int lane, co
     for (int j = 0; j < nmax; ++j) {
         if (j < qn) {
             const float2 e = q[j * 32 + lane];
-            cum = __fadd_rn(cum, pk_integral(e.x, e.y, table));
+            // OnHit_sphere_cumulate: multiply and accumulate are ONE fma in the reference's SASS
+            cum = __fmaf_rn(pk_lerp(e.x, e.y, table), __fmul_rn(e.y, e.y), cum);
         }
     }
     __syncwarp();

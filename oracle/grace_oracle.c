@@ -369,7 +369,7 @@ ORC_API const double* orc_kernel_table(void) { return kernel_table; }
 /* cuda/functors/trace.cuh:183-186 + generic/interpolate.h:11-39 (device form):
  *   ir = 1/h; x = (sqrt(b2)*ir)*50; i = trunc(x) clamped; t = (double)x - i;
  *   y = fma(t, T[i+1]-T[i], T[i]) in double; integral = (float)y * (ir*ir). */
-static inline float kernel_integral(float b2, float h)
+static inline float kernel_lerp(float b2, float h, float* ir2_out)
 {
     float ir = 1.0f / h;
     float x = (sqrtf(b2) * ir) * 50.0f;
@@ -380,7 +380,28 @@ static inline float kernel_integral(float b2, float h)
     double y0 = kernel_table[i], y1 = kernel_table[i + 1];
     double t = (double)x - (double)i;
     double y = fma(t, y1 - y0, y0);
-    return (float)y * (ir * ir);
+    *ir2_out = ir * ir;
+    return (float)y;
+}
+
+/* Per-hit integral as stored by OnHit_sphere_individual (cuda/functors/trace.cuh:221-228):
+ * integral = (float)y * (ir*ir), one FMUL. */
+static inline float kernel_integral(float b2, float h)
+{
+    float ir2;
+    float y = kernel_lerp(b2, h, &ir2);
+    return y * ir2;
+}
+
+/* OnHit_sphere_cumulate (cuda/functors/trace.cuh:183-191): `integral *= ir*ir;
+ * ray_data.data += integral;` is contracted by nvcc into ONE fused multiply-add,
+ * data = fma((float)y, ir*ir, data) (SASS of the reference's cumulative trace kernel:
+ * F2F.F32.F64 ; FFMA R27, R8, R15, R27). */
+static inline float kernel_accumulate(float cum, float b2, float h)
+{
+    float ir2;
+    float y = kernel_lerp(b2, h, &ir2);
+    return fmaf(y, ir2, cum);
 }
 
 ORC_API float orc_kernel_integral(float b2, float h) { return kernel_integral(b2, h); }
@@ -454,7 +475,7 @@ ORC_API int orc_trace(const float* rays7, long n_rays, const float* s4,
                         float b2, dot;
                         if (sphere_hit(&rays[l], s, &b2, &dot)) {
                             if (mode == 0) cnt[l]++;
-                            else if (mode == 1) cum[l] += kernel_integral(b2, s[3]);
+                            else if (mode == 1) cum[l] = kernel_accumulate(cum[l], b2, s[3]);
                             else {
                                 int32_t w = cur[l]++;
                                 hit_idx[w] = first + i;
@@ -490,7 +511,7 @@ ORC_API void orc_brute(const float* rays7, long n_rays, const float* s4, long n,
             float b2, dot;
             if (sphere_hit(&rays[r], s4 + 4 * i, &b2, &dot)) {
                 if (mode == 0) ++c;
-                else cum += kernel_integral(b2, s4[4 * i + 3]);
+                else cum = kernel_accumulate(cum, b2, s4[4 * i + 3]);
             }
         }
         if (mode == 0) out_counts[r] = c; else out_cum[r] = cum;
