@@ -19,6 +19,7 @@ import math
 import torch
 
 from . import _lib
+from ._dist import sharded_trace, tiles_of_rank, take_local, scatter_back  # noqa: F401
 
 __all__ = [
     "Tree", "RaySortType", "Octants", "N_table", "kernel_integral_table",
@@ -29,7 +30,7 @@ __all__ = [
     "min_vec3", "max_vec3", "min_max_x", "min_vec4", "max_vec4",
     "uniform_random_rays", "uniform_random_rays_single_octant", "one_to_many_rays",
     "plane_parallel_random_rays", "orthographic_projection_rays", "pinhole_camera_rays",
-    "healpix_rays", "synth_gadget_spheres", "context", "lib", "build_tree", "set_trace_mode", "set_trace_budget", "device_error",
+    "healpix_rays", "synth_gadget_spheres", "context", "lib", "build_tree", "set_trace_mode", "set_trace_budget", "device_error", "sharded_trace", "tiles_of_rank",
 ]
 
 _c = ctypes

@@ -1,0 +1,106 @@
+// grace/cuda/trace_sph.cuh -- SPH trace API (reference: cuda/trace_sph.cuh:22-241).
+#pragma once
+#include "grace/cuda/nodes.h"
+#include "grace/generic/raydata.h"
+#include "grace/ray.h"
+
+namespace grace {
+
+const static int N_table = 51;
+
+// Line integrals of the Gadget-2 cubic spline kernel at impact parameter b/h = i/50.
+template <typename Real>
+struct KernelIntegrals {
+    static const Real* table_ptr()
+    {
+        static Real t[N_table];
+        static bool init = false;
+        if (!init) {
+            int n = 0;
+            const double* src = grace_b200_kernel_integral_table(&n);
+            for (int i = 0; i < N_table; ++i) t[i] = static_cast<Real>(src[i]);
+            init = true;
+        }
+        return t;
+    }
+};
+
+namespace detail {
+inline const grace_b200_ray* rays_ptr(const Ray* r) { return reinterpret_cast<const grace_b200_ray*>(r); }
+}
+
+// All throw std::invalid_argument unless d_rays.size() % 32 == 0.
+template <typename RayVec, typename SphereVec, typename IntVec>
+GRACE_HOST void trace_hitcounts_sph(const RayVec& d_rays, const SphereVec& d_spheres, const Tree& d_tree,
+                                    IntVec& d_hit_counts)
+{
+    const grace_b200_tree t = detail::tree_view(d_tree);
+    GRACE_B200_CHECK(grace_b200_trace_hitcounts_f4(
+        detail::context(), detail::rays_ptr(detail::raw(d_rays.data())), d_rays.size(),
+        reinterpret_cast<const float*>(detail::raw(d_spheres.data())), d_spheres.size(), &t,
+        detail::raw(d_hit_counts.data()), nullptr));
+}
+
+template <typename RayVec, typename SphereVec, typename RealVec>
+GRACE_HOST void trace_cumulative_sph(const RayVec& d_rays, const SphereVec& d_spheres, const Tree& d_tree,
+                                     RealVec& d_cumulated)
+{
+    const grace_b200_tree t = detail::tree_view(d_tree);
+    GRACE_B200_CHECK(grace_b200_trace_cumulative_f4(
+        detail::context(), detail::rays_ptr(detail::raw(d_rays.data())), d_rays.size(),
+        reinterpret_cast<const float*>(detail::raw(d_spheres.data())), d_spheres.size(), &t,
+        detail::raw(d_cumulated.data()), nullptr));
+}
+
+namespace detail {
+template <typename RayVec, typename SphereVec, typename IntVec, typename IdxVec, typename RealVec>
+inline void trace_lists(const RayVec& d_rays, const SphereVec& d_spheres, const Tree& d_tree, IntVec& d_ray_offsets,
+                        IdxVec& d_hit_indices, RealVec& d_hit_integrals, RealVec& d_hit_distances, bool sentinels,
+                        int index_sentinel, float integral_sentinel, float distance_sentinel)
+{
+    const grace_b200_tree t = tree_view(d_tree);
+    const grace_b200_ray* rp = rays_ptr(raw(d_rays.data()));
+    const float* sp = reinterpret_cast<const float*>(raw(d_spheres.data()));
+    long long total = 0;
+    GRACE_B200_CHECK(grace_b200_trace_hits_count_f4(context(), rp, d_rays.size(), sp, d_spheres.size(), &t,
+                                                    sentinels ? 1 : 0, raw(d_ray_offsets.data()), &total, nullptr));
+    if (sentinels) {
+        d_hit_indices.resize((size_t)total, index_sentinel);
+        d_hit_integrals.resize((size_t)total, integral_sentinel);
+        d_hit_distances.resize((size_t)total, distance_sentinel);
+    } else {
+        d_hit_indices.resize((size_t)total);
+        d_hit_integrals.resize((size_t)total);
+        d_hit_distances.resize((size_t)total);
+    }
+    if (total > 0)
+        GRACE_B200_CHECK(grace_b200_trace_hits_fill_f4(context(), rp, d_rays.size(), sp, d_spheres.size(), &t,
+                                                       raw(d_ray_offsets.data()), raw(d_hit_indices.data()),
+                                                       raw(d_hit_integrals.data()), raw(d_hit_distances.data()),
+                                                       nullptr));
+}
+} // namespace detail
+
+// d_ray_offsets must hold one int per ray; the three hit vectors are resized by the call.
+template <typename RayVec, typename SphereVec, typename IntVec, typename IdxVec, typename RealVec>
+GRACE_HOST void trace_sph(const RayVec& d_rays, const SphereVec& d_spheres, const Tree& d_tree, IntVec& d_ray_offsets,
+                          IdxVec& d_hit_indices, RealVec& d_hit_integrals, RealVec& d_hit_distances)
+{
+    detail::trace_lists(d_rays, d_spheres, d_tree, d_ray_offsets, d_hit_indices, d_hit_integrals, d_hit_distances,
+                        false, 0, 0.f, 0.f);
+}
+
+// Each ray's segment ends with one slot holding the sentinels.
+template <typename RayVec, typename SphereVec, typename IntVec, typename IdxVec, typename RealVec, typename Real>
+GRACE_HOST void trace_with_sentinels_sph(const RayVec& d_rays, const SphereVec& d_spheres, const Tree& d_tree,
+                                         IntVec& d_ray_offsets, IdxVec& d_hit_indices, const int index_sentinel,
+                                         RealVec& d_hit_integrals, const Real integral_sentinel,
+                                         RealVec& d_hit_distances, const Real distance_sentinel)
+{
+    // Sentinel-filled resize of possibly non-empty vectors: start from empty like a fresh call.
+    d_hit_indices.resize(0); d_hit_integrals.resize(0); d_hit_distances.resize(0);
+    detail::trace_lists(d_rays, d_spheres, d_tree, d_ray_offsets, d_hit_indices, d_hit_integrals, d_hit_distances,
+                        true, index_sentinel, (float)integral_sentinel, (float)distance_sentinel);
+}
+
+} // namespace grace

@@ -1,0 +1,197 @@
+// shim_tests.cpp -- the reference's own tests, re-expressed against include/grace (the C++
+// drop-in API of this repo) -- so they read like GRACE's tests/ programs:
+//   morton_key/30bit_key.cu, 63bit_key.cu        -> test_morton_kat
+//   tree_traversal/tree_traversal.cu:46-121       -> test_tree_traversal
+//   integrate/integrate.cu:48-101                 -> test_integrate
+//   distance_sort/distance_sort.cu:22-79,125-148  -> test_distance_sort
+// plus the argument-error behaviour (std::invalid_argument).  Plain host C++: the CUDA work
+// happens behind the C ABI in libgrace_b200.so.
+#include "grace/cuda/build_sph.cuh"
+#include "grace/cuda/gen_rays.cuh"
+#include "grace/cuda/sort.cuh"
+#include "grace/cuda/trace_sph.cuh"
+#include "grace/cuda/util/extrema.cuh"
+#include "grace/generic/intersect.h"
+#include "grace/generic/morton.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <stdexcept>
+#include <vector>
+
+static unsigned hash_u32(unsigned a)     // Wang/Jenkins integer hash
+{
+    a = (a + 0x7ed55d16) + (a << 12); a = (a ^ 0xc761c23c) ^ (a >> 19);
+    a = (a + 0x165667b1) + (a << 5);  a = (a + 0xd3a2646c) ^ (a << 9);
+    a = (a + 0xfd7046c5) + (a << 3);  a = (a ^ 0xb55a4f09) ^ (a >> 16);
+    return a;
+}
+static float u01(unsigned i, unsigned k) { return (hash_u32(i * 4u + k) >> 8) * (1.0f / 16777216.0f); }
+
+static std::vector<float4> random_spheres(size_t n, float4 lo, float4 hi)
+{
+    std::vector<float4> s(n);
+    for (size_t i = 0; i < n; ++i) {
+        s[i].x = lo.x + (hi.x - lo.x) * u01((unsigned)i, 0);
+        s[i].y = lo.y + (hi.y - lo.y) * u01((unsigned)i, 1);
+        s[i].z = lo.z + (hi.z - lo.z) * u01((unsigned)i, 2);
+        s[i].w = lo.w + (hi.w - lo.w) * u01((unsigned)i, 3);
+    }
+    return s;
+}
+
+// tests/helper/tree.cuh:29-43
+static void build_tree(grace::device_vector<float4>& spheres, float4 lo, float4 hi, grace::Tree& tree)
+{
+    grace::device_vector<float> deltas(spheres.size() + 1);
+    grace::morton_keys30_sort_sph(spheres, make_float3(lo.x, lo.y, lo.z), make_float3(hi.x, hi.y, hi.z));
+    grace::euclidean_deltas_sph(spheres, deltas);
+    grace::ALBVH_sph(spheres, deltas, tree);
+}
+
+// device arithmetic of sphere_hit (FMA contraction as in the CUDA build)
+static bool sphere_hit_fma(const grace::Ray& r, const float4& s)
+{
+    const float px = s.x - r.ox, py = s.y - r.oy, pz = s.z - r.oz;
+    float dot = py * r.dy; dot = fmaf(px, r.dx, dot); dot = fmaf(pz, r.dz, dot);
+    const float bx = fmaf(-r.dx, dot, px), by = fmaf(-r.dy, dot, py), bz = fmaf(-r.dz, dot, pz);
+    float b2 = by * by; b2 = fmaf(bx, bx, b2); b2 = fmaf(bz, bz, b2);
+    return !(b2 >= s.w * s.w) && !(dot < 0.f) && !(dot >= r.length);
+}
+
+static int test_morton_kat()
+{
+    using namespace grace;
+    bool ok = detail::space_by_two_10bit(309u) == 16814145u && detail::space_by_two_10bit(942u) == 153125448u &&
+              detail::space_by_two_10bit(619u) == 134513161u &&
+              morton_key((uinteger32)309, (uinteger32)942, (uinteger32)619) == 861117685u &&
+              morton_key((uinteger64)1365301, (uinteger64)2014126, (uinteger64)1683051) == 8995068606879603957ull;
+    return ok ? 0 : 1;
+}
+
+static int test_tree_traversal(size_t N, size_t N_rays, int max_per_leaf)
+{
+    const float4 lo = make_float4(-1E4f, -1E4f, -1E4f, 80.f), hi = make_float4(1E4f, 1E4f, 1E4f, 400.f);
+    grace::device_vector<float4> d_spheres(random_spheres(N, lo, hi));
+    grace::device_vector<grace::Ray> d_rays(N_rays);
+    grace::device_vector<int> d_hit_counts(N_rays);
+    grace::Tree d_tree(N, max_per_leaf);
+    build_tree(d_spheres, lo, hi, d_tree);
+    grace::uniform_random_rays(d_rays, 0.f, 0.f, 0.f, 2E4f);
+    grace::trace_hitcounts_sph(d_rays, d_spheres, d_tree, d_hit_counts);
+
+    const std::vector<float4> h_spheres = d_spheres.to_host();
+    const std::vector<grace::Ray> h_rays = d_rays.to_host();
+    const std::vector<int> h_counts = d_hit_counts.to_host();
+    size_t failed_exact = 0, failed_host_form = 0;
+    double total = 0;
+#pragma omp parallel for reduction(+ : failed_exact, failed_host_form, total)
+    for (long ri = 0; ri < (long)N_rays; ++ri) {
+        int hits = 0, hits_host = 0;
+        float b2, d;
+        for (size_t si = 0; si < N; ++si) {
+            hits += sphere_hit_fma(h_rays[ri], h_spheres[si]);
+            hits_host += grace::sphere_hit(h_rays[ri], h_spheres[si], b2, d);
+        }
+        failed_exact += hits != h_counts[ri];
+        failed_host_form += hits_host != h_counts[ri];
+        total += h_counts[ri];
+    }
+    std::printf("  tree_traversal: N=%zu rays=%zu mean hits %.2f, mismatching rays: %zu (device arithmetic) %zu (host arithmetic)\n",
+                N, N_rays, total / N_rays, failed_exact, failed_host_form);
+    return (failed_exact == 0 && failed_host_form <= 2) ? 0 : 1;
+}
+
+static int test_integrate()
+{
+    const size_t N = 2;
+    const float radius = 0.2f;
+    std::vector<float4> h(2);
+    h[0] = make_float4(-0.5f, -0.5f, -0.5f, radius);
+    h[1] = make_float4(0.5f, 0.5f, 0.5f, radius);
+    grace::device_vector<float4> d_spheres(h);
+    grace::Tree d_tree(N, 1);
+    build_tree(d_spheres, make_float4(-1, -1, -1, 0), make_float4(1, 1, 1, 0), d_tree);
+    const int n_side = 512;
+    // plane_parallel_rays_z, tests/helper/rays.cuh:98-123
+    const float span = 2.f + 2 * radius;
+    const float3 base = make_float3(-1.f - radius, 1.f + radius, 1.f + radius);
+    const float3 w = make_float3(span, 0.f, 0.f), hh = make_float3(0.f, -span, 0.f);
+    grace::device_vector<grace::Ray> d_rays;
+    grace::plane_parallel_random_rays(d_rays, n_side, n_side, base, w, hh, 2 * span);
+    grace::device_vector<float> d_integrals((size_t)n_side * n_side);
+    grace::trace_cumulative_sph(d_rays, d_spheres, d_tree, d_integrals);
+    const std::vector<float> v = d_integrals.to_host();
+    double sum = 0;
+    for (float x : v) sum += x;
+    const double integrated = sum * (span / n_side) * (span / n_side) / N;
+    std::printf("  integrate: normalised volume integral %.6f\n", integrated);
+    return std::fabs(1.0 - integrated) < 5e-4 ? 0 : 1;
+}
+
+static int test_distance_sort()
+{
+    const size_t N = 100000, N_rays = 80000;
+    const float4 lo = make_float4(0, 0, 0, 0), hi = make_float4(1, 1, 1, 0.05f);
+    grace::device_vector<float4> d_spheres(random_spheres(N, lo, hi));
+    grace::Tree d_tree(N, 32);
+    build_tree(d_spheres, lo, hi, d_tree);
+    grace::device_vector<grace::Ray> d_rays(N_rays);
+    grace::uniform_random_rays(d_rays, 0.5f, 0.5f, 0.5f, 2.f);
+    grace::device_vector<int> d_offsets(N_rays), d_indices;
+    grace::device_vector<float> d_integrals, d_distances;
+    grace::trace_sph(d_rays, d_spheres, d_tree, d_offsets, d_indices, d_integrals, d_distances);
+    grace::sort_by_distance(d_distances, d_offsets, d_indices, d_integrals);
+    const std::vector<int> off = d_offsets.to_host();
+    const std::vector<float> dist = d_distances.to_host();
+    size_t failures = 0;
+    for (size_t r = 0; r < N_rays; ++r) {
+        const size_t b = off[r], e = (r + 1 < N_rays) ? (size_t)off[r + 1] : dist.size();
+        for (size_t i = b; i < e; ++i) {
+            if (dist[i] < 0) ++failures;
+            if (i > b && dist[i] < dist[i - 1]) ++failures;
+        }
+    }
+    std::printf("  distance_sort: %zu hits over %zu rays, %zu ordering failures\n", dist.size(), N_rays, failures);
+    return failures == 0 && !dist.empty() ? 0 : 1;
+}
+
+static int test_errors()
+{
+    int bad = 0;
+    std::vector<float4> h = random_spheres(64, make_float4(0, 0, 0, 0.01f), make_float4(1, 1, 1, 0.1f));
+    grace::device_vector<float4> d_spheres(h);
+    grace::device_vector<float> deltas(65);
+    grace::euclidean_deltas_sph(d_spheres, deltas);
+    try { grace::Tree t(64, 64); grace::ALBVH_sph(d_spheres, deltas, t); ++bad; }          // albvh.cuh:795-799
+    catch (const std::invalid_argument&) {}
+    grace::Tree tree(64, 8);
+    grace::ALBVH_sph(d_spheres, deltas, tree);
+    grace::device_vector<grace::Ray> d_rays(33);
+    grace::device_vector<int> counts(33);
+    try { grace::trace_hitcounts_sph(d_rays, d_spheres, tree, counts); ++bad; }            // bintree_trace.cuh:231-238
+    catch (const std::invalid_argument&) {}
+    try { grace::one_to_many_rays(d_rays, 0.f, 0.f, 0.f, d_spheres, (grace::RaySortType)7); ++bad; }   // gen_rays.cuh:124-130
+    catch (const std::invalid_argument&) {}
+    return bad;
+}
+
+int main(int argc, char** argv)
+{
+    const size_t N = argc > 1 ? std::strtoul(argv[1], 0, 10) : 200000;
+    const size_t N_rays = argc > 2 ? 32 * std::strtoul(argv[2], 0, 10) : 32 * 200;
+    int failed = 0;
+    struct { const char* name; int rc; } results[] = {
+        { "morton_key KAT", test_morton_kat() },
+        { "tree_traversal", test_tree_traversal(N, N_rays, 32) },
+        { "integrate", test_integrate() },
+        { "distance_sort", test_distance_sort() },
+        { "argument errors", test_errors() },
+    };
+    for (auto& r : results) {
+        std::printf("%s %s\n", r.rc == 0 ? "PASSED" : "FAILED", r.name);
+        failed += r.rc != 0;
+    }
+    return failed ? EXIT_FAILURE : EXIT_SUCCESS;
+}

@@ -1,0 +1,19 @@
+"""Runs the C++ drop-in API tests (tests/cpp/shim_tests.cpp: the reference's own test programs
+re-expressed against include/grace) on the GPU."""
+import os
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "tests", "cpp", "shim_tests")
+
+
+def test_cpp_shim_programs(gb):
+    if not os.path.exists(BIN):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "cpp")])
+    out = subprocess.run([BIN, "200000", "200"], capture_output=True, text=True, timeout=600)
+    print(out.stdout[-3000:], out.stderr[-2000:])
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert out.stdout.count("PASSED") == 5 and "FAILED" not in out.stdout
