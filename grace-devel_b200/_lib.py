@@ -9,7 +9,8 @@ import re
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgrace_b200.so")
+# GRACE_B200_LIB: development knob to load an A/B build of the same library (scripts/ab_variants.sh)
+LIB_PATH = os.environ.get("GRACE_B200_LIB") or os.path.join(_HERE, "libgrace_b200.so")
 HEADER_PATH = os.path.join(_HERE, "..", "include", "grace_b200.h")
 
 

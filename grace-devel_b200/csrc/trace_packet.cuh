@@ -35,10 +35,20 @@
 
 constexpr int PK_THREADS = 128;
 constexpr int PK_WARPS = PK_THREADS / 32;
-constexpr int PK_MIN_BLOCKS = 5;     // register budget: 65536 / (5 * 128) = 102
+#ifndef PK_MIN_BLOCKS_V
+#define PK_MIN_BLOCKS_V 5
+#endif
+constexpr int PK_MIN_BLOCKS = PK_MIN_BLOCKS_V;   // register budget: 65536 / (5 * 128) = 102
 constexpr int PK_STACK = 96;         // reference STACK_SIZE is 64 (kernel_config.h:13)
 constexpr int PK_QD = 8;             // FIFO depth per lane
-constexpr int PK_BATCH = 8;          // leaves fetched together
+#ifndef PK_BATCH_V
+#define PK_BATCH_V 8
+#endif
+constexpr int PK_BATCH = PK_BATCH_V; // leaves fetched together
+#ifndef PK_ROOM_MIN_V
+#define PK_ROOM_MIN_V 2
+#endif
+constexpr int PK_ROOM_MIN = PK_ROOM_MIN_V;   // flush when fewer than this many pushes are guaranteed to fit
 
 template <int MODE, int M4>
 struct PkWarp {
@@ -50,6 +60,7 @@ struct PkWarp {
     int2 stack[PK_STACK];                      // {node or leaf index, lane mask}
     float ir[NEED_Q ? M4 : 4];                 // 1/h of the staged spheres
     float2 q[NEED_Q ? PK_QD * 32 : 2];         // FIFO {b2, 1/h}, [slot][lane]
+    unsigned char cells[NEED_Q ? PK_QD * 32 : 4];   // occupied FIFO cells, slot-major (flush work list)
     int idx[NEED_I ? M4 : 4];                  // primitive index of the staged spheres
     float2 q2[NEED_I ? PK_QD * 32 : 2];        // FIFO {distance, index bits}
 };
@@ -69,73 +80,99 @@ __device__ __forceinline__ void prefetch_l1(const void* p)
 }
 
 // cuda/functors/trace.cuh:183-186 + generic/interpolate.h:15-38 with 1/h precomputed (the
-// same IEEE quotient the reference forms per hit).
-__device__ __forceinline__ float pk_lerp(float b2, float ir, const double* table)
+// same IEEE quotient the reference forms per hit).  table[i] = {T[i], T[i+1] - T[i]}: the
+// reference forms the same double difference per hit.  t = x - i is exact in float
+// (Sterbenz: i <= x < i + 1) so it equals the reference's (double)x - (double)i.
+__device__ __forceinline__ float pk_lerp(float b2, float ir, const double2* table)
 {
-    float x = __fmul_rn(__fmul_rn(__fsqrt_rn(b2), ir), 50.0f);
-    int i = __float2int_rz(x);
-    if (i >= N_TABLE - 1) { x = (float)(N_TABLE - 1); i = N_TABLE - 2; }
-    i = max(i, 0);
-    const double y0 = table[i], y1 = table[i + 1];
-    const double t = __dsub_rn((double)x, (double)i);
-    return (float)__fma_rn(t, __dsub_rn(y1, y0), y0);
-}
-// per-hit value as stored (OnHit_sphere_individual): one FMUL
-__device__ __forceinline__ float pk_integral(float b2, float ir, const double* table)
-{
-    return __fmul_rn(pk_lerp(b2, ir, table), __fmul_rn(ir, ir));
+    const float x = __fmul_rn(__fmul_rn(__fsqrt_rn(b2), ir), 50.0f);
+    const int i_raw = __float2int_rz(x);
+    const int i = min(max(i_raw, 0), N_TABLE - 2);
+    const float t = i_raw >= N_TABLE - 1 ? 1.0f : __fsub_rn(x, (float)i);
+    const double2 e = table[i];
+    return (float)__fma_rn((double)t, e.y, e.x);
 }
 
-// Evaluate a lane's FIFO in order.  Real calls (not inlined): the kernel has ~10 call sites
-// and each copy is ~150 SASS instructions.
-__device__ __noinline__ float pk_flush_cum(const float2* q, int qn, int lane, const double* table, float cum)
+// Everything a packet accumulates per lane, plus where hit lists go.
+struct PkAcc {
+    int count; float cum; int cursor;
+    int qn;       // entries in this lane's FIFO
+    int room;     // warp-uniform: pushes per lane guaranteed to fit before the next check
+    int* hit_idx; float* hit_integral; float* hit_dist;
+};
+
+// Evaluate all FIFOs.  The on-hit work (sqrt, double-precision lerp) is spread evenly over
+// the 32 lanes whatever the per-ray hit counts are: the occupied cells are listed slot-major
+// (conflict-free), each lane evaluates every 32nd listed cell and writes {W, 1/h^2} back in
+// place; then every lane folds ITS OWN cells in FIFO order -- ascending primitive order, one
+// FFMA each, exactly the reference's accumulation (OnHit_sphere_cumulate is one fma in SASS).
+// Real calls (not inlined): the kernel has ~10 call sites.
+template <int MODE, int M4>
+__device__ __forceinline__ void pk_flush_eval(PkWarp<MODE, M4>& W, int qn, int lane, unsigned lt, const double2* table)
 {
     __syncwarp();       // entries may have been written by other lanes (transposed leaves)
-    const int nmax = __reduce_max_sync(0xffffffffu, qn);
-    for (int j = 0; j < nmax; ++j) {
-        if (j < qn) {
-            const float2 e = q[j * 32 + lane];
-            // OnHit_sphere_cumulate: multiply and accumulate are ONE fma in the reference's SASS
-            cum = __fmaf_rn(pk_lerp(e.x, e.y, table), __fmul_rn(e.y, e.y), cum);
-        }
+    int total = 0;
+#pragma unroll
+    for (int j = 0; j < PK_QD; ++j) {
+        const unsigned m = __ballot_sync(0xffffffffu, j < qn);
+        if (j < qn) W.cells[total + __popc(m & lt)] = (unsigned char)(j * 32 + lane);
+        total += __popc(m);
     }
+    __syncwarp();
+    for (int k = lane; k < total; k += 32) {
+        const int c = W.cells[k];
+        const float2 e = W.q[c];
+        const float w = pk_lerp(e.x, e.y, table);
+        const float ir2 = __fmul_rn(e.y, e.y);
+        // per-hit value as stored (OnHit_sphere_individual): one FMUL
+        W.q[c] = MODE == MODE_FILL ? make_float2(__fmul_rn(w, ir2), 0.f) : make_float2(w, ir2);
+    }
+    __syncwarp();
+}
+
+template <int MODE, int M4>
+__device__ __noinline__ float pk_flush_cum(PkWarp<MODE, M4>& W, int qn, float cum, int lane, unsigned lt, const double2* table)
+{
+    pk_flush_eval<MODE, M4>(W, qn, lane, lt, table);
+#pragma unroll
+    for (int j = 0; j < PK_QD; ++j)
+        if (j < qn) { const float2 e = W.q[j * 32 + lane]; cum = __fmaf_rn(e.x, e.y, cum); }
     __syncwarp();
     return cum;
 }
 
-__device__ __noinline__ int pk_flush_fill(const float2* q, const float2* q2, int qn, int lane,
-                                          const double* table, int cursor, int* hit_idx,
-                                          float* hit_integral, float* hit_dist)
+template <int MODE, int M4>
+__device__ __noinline__ int pk_flush_fill(PkWarp<MODE, M4>& W, int qn, int cursor, int lane, unsigned lt, const double2* table,
+                                          int* hit_idx, float* hit_integral, float* hit_dist)
 {
-    __syncwarp();
-    const int nmax = __reduce_max_sync(0xffffffffu, qn);
-    for (int j = 0; j < nmax; ++j) {
-        if (j < qn) {
-            const float2 e = q[j * 32 + lane];
-            const float2 e2 = q2[j * 32 + lane];
-            hit_idx[cursor] = __float_as_int(e2.y);
-            hit_integral[cursor] = pk_integral(e.x, e.y, table);
-            hit_dist[cursor] = e2.x;
-            ++cursor;
-        }
+    pk_flush_eval<MODE, M4>(W, qn, lane, lt, table);
+    for (int j = 0; j < qn; ++j) {
+        const float2 e2 = W.q2[j * 32 + lane];
+        hit_idx[cursor] = __float_as_int(e2.y);
+        hit_integral[cursor] = W.q[j * 32 + lane].x;
+        hit_dist[cursor] = e2.x;
+        ++cursor;
     }
     __syncwarp();
     return cursor;
 }
 
-// Everything a packet accumulates per lane, plus where hit lists go.
-struct PkAcc {
-    int count; float cum; int cursor; int qn;
-    int* hit_idx; float* hit_integral; float* hit_dist;
-};
-
 template <int MODE, int M4>
-__device__ __forceinline__ void pk_flush(PkWarp<MODE, M4>& W, PkAcc& A, int lane, const double* table)
+__device__ __forceinline__ void pk_flush(PkWarp<MODE, M4>& W, PkAcc& A, int lane, unsigned lt, const double2* table)
 {
-    if (MODE == MODE_CUMULATIVE) A.cum = pk_flush_cum(W.q, A.qn, lane, table, A.cum);
+    if (MODE == MODE_CUMULATIVE) A.cum = pk_flush_cum<MODE, M4>(W, A.qn, A.cum, lane, lt, table);
     if (MODE == MODE_FILL)
-        A.cursor = pk_flush_fill(W.q, W.q2, A.qn, lane, table, A.cursor, A.hit_idx, A.hit_integral, A.hit_dist);
+        A.cursor = pk_flush_fill<MODE, M4>(W, A.qn, A.cursor, lane, lt, table, A.hit_idx, A.hit_integral, A.hit_dist);
     A.qn = 0;
+    A.room = PK_QD;
+}
+
+// Re-derive how many pushes per lane are guaranteed to fit; flush when that is too few.
+template <int MODE, int M4>
+__device__ __forceinline__ void pk_room(PkWarp<MODE, M4>& W, PkAcc& A, int lane, unsigned lt, const double2* table)
+{
+    A.room = PK_QD - __reduce_max_sync(0xffffffffu, A.qn);
+    if (A.room < PK_ROOM_MIN) pk_flush<MODE, M4>(W, A, lane, lt, table);
 }
 
 // ---- conservative bound of a whole packet --------------------------------------------
@@ -229,26 +266,42 @@ __device__ __forceinline__ bool pk_test(const float4 s, float ox, float oy, floa
     return !(b2 >= s.w) && !(dot < 0.0f) && !(dot >= len);
 }
 
-// Dense leaf: every lane tests every staged sphere against its own ray.
+// Dense leaf: every lane tests every staged sphere against its own ray.  Hits go to the
+// lane's FIFO; the loop body has no vote and no branch: it runs for `room` spheres, the
+// number of pushes every lane's FIFO is known to have space for, and only then looks at the
+// fill levels again.
 template <int MODE, int M4, bool COMMON>
 __device__ __forceinline__ void pk_leaf_dense(PkWarp<MODE, M4>& W, int n_kept, const grace_b200_ray& ray,
-                                              int lane, bool lane_on, PkAcc& A, const double* table)
+                                              int lane, unsigned lt, bool lane_on, PkAcc& A, const double2* table)
 {
-#pragma unroll 2
-    for (int i = 0; i < n_kept; ++i) {
-        const float4 s = W.prims[i];
-        float b2, dot;
-        const bool hit = pk_test<COMMON>(s, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, ray.length, b2, dot) && lane_on;
-        if (MODE == MODE_COUNT) {
-            A.count += (int)hit;
-        } else {
-            if (hit) {
-                W.q[A.qn * 32 + lane] = make_float2(b2, W.ir[i]);
-                if (MODE == MODE_FILL) W.q2[A.qn * 32 + lane] = make_float2(dot, __int_as_float(W.idx[i]));
-                ++A.qn;
-            }
-            if (__any_sync(0xffffffffu, A.qn == PK_QD)) pk_flush<MODE, M4>(W, A, lane, table);
+    if (MODE == MODE_COUNT) {
+#pragma unroll 4
+        for (int i = 0; i < n_kept; ++i) {
+            float b2, dot;
+            A.count += (int)(pk_test<COMMON>(W.prims[i], ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz,
+                                             ray.length, b2, dot) && lane_on);
         }
+        return;
+    }
+    int i = 0;
+    while (i < n_kept) {
+        if (A.room == 0) pk_room<MODE, M4>(W, A, lane, lt, table);
+        const int n = min(n_kept - i, A.room);
+        A.room -= n;
+        const int end = i + n;
+        int qn = A.qn;
+#pragma unroll 4
+        for (; i < end; ++i) {
+            const float4 s = W.prims[i];
+            float b2, dot;
+            const bool hit = pk_test<COMMON>(s, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, ray.length, b2, dot) && lane_on;
+            if (hit) {
+                W.q[qn * 32 + lane] = make_float2(b2, W.ir[i]);
+                if (MODE == MODE_FILL) W.q2[qn * 32 + lane] = make_float2(dot, __int_as_float(W.idx[i]));
+                ++qn;
+            }
+        }
+        A.qn = qn;
     }
 }
 
@@ -257,7 +310,7 @@ __device__ __forceinline__ void pk_leaf_dense(PkWarp<MODE, M4>& W, int n_kept, c
 // sphere order.
 template <int MODE, int M4, bool COMMON>
 __device__ __forceinline__ void pk_leaf_sparse(PkWarp<MODE, M4>& W, unsigned mask, int n_kept, int lane,
-                                               unsigned lt, PkAcc& A, const double* table)
+                                               unsigned lt, PkAcc& A, const double2* table)
 {
     for (int base = 0; base < n_kept; base += 32) {
         const int j = base + lane;
@@ -285,7 +338,7 @@ __device__ __forceinline__ void pk_leaf_sparse(PkWarp<MODE, M4>& W, unsigned mas
                 int qn_r = __shfl_sync(0xffffffffu, A.qn, r);
                 int done = 0;
                 while (done < nh) {
-                    if (qn_r == PK_QD) { pk_flush<MODE, M4>(W, A, lane, table); qn_r = 0; }
+                    if (qn_r == PK_QD) { pk_flush<MODE, M4>(W, A, lane, lt, table); qn_r = 0; }
                     const int take = min(PK_QD - qn_r, nh - done);
                     if (hit && rank >= done && rank < done + take) {
                         W.q[(qn_r + rank - done) * 32 + r] = make_float2(b2, ir);
@@ -294,12 +347,10 @@ __device__ __forceinline__ void pk_leaf_sparse(PkWarp<MODE, M4>& W, unsigned mas
                     if (lane == r) A.qn += take;
                     qn_r += take;
                     done += take;
+                    A.room = min(A.room, PK_QD - qn_r);
                 }
             }
         }
-    }
-    if (MODE != MODE_COUNT) {
-        if (__any_sync(0xffffffffu, A.qn == PK_QD)) pk_flush<MODE, M4>(W, A, lane, table);
     }
 }
 
@@ -348,11 +399,14 @@ trace_packet_kernel(const PkArgs P, const PkTasks T)
     using Warp = PkWarp<MODE, M4>;
     constexpr bool NEED_Q = Warp::NEED_Q;
     extern __shared__ __align__(16) unsigned char pk_smem[];
-    double* s_table = (double*)pk_smem;
+    double2* s_table = (double2*)pk_smem;     // {T[i], T[i+1] - T[i]}
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    Warp& W = *((Warp*)(pk_smem + 52 * sizeof(double)) + warp);
+    Warp& W = *((Warp*)(pk_smem + 52 * sizeof(double2)) + warp);
     if (NEED_Q) {
-        for (int i = threadIdx.x; i < N_TABLE; i += PK_THREADS) s_table[i] = c_kernel_table[i];
+        for (int i = threadIdx.x; i < N_TABLE; i += PK_THREADS) {
+            const double y0 = c_kernel_table[i], y1 = c_kernel_table[min(i + 1, N_TABLE - 1)];
+            s_table[i] = make_double2(y0, __dsub_rn(y1, y0));
+        }
         __syncthreads();
     }
     const float4* __restrict__ spheres = P.spheres;
@@ -397,7 +451,7 @@ trace_packet_kernel(const PkArgs P, const PkTasks T)
         // every lane must execute every shuffle)
         const bool common = __all_sync(0xffffffffu, (ray.ox == B.ocx) & (ray.oy == B.ocy) & (ray.oz == B.ocz));
         PkAcc A;
-        A.count = 0; A.cum = 0.0f; A.cursor = 0; A.qn = 0;
+        A.count = 0; A.cum = 0.0f; A.cursor = 0; A.qn = 0; A.room = PK_QD;
         A.hit_idx = P.hit_idx; A.hit_integral = P.hit_integral; A.hit_dist = P.hit_dist;
         int sp = 0;
         int top = root;
@@ -441,7 +495,7 @@ trace_packet_kernel(const PkArgs P, const PkTasks T)
                 rslot = __shfl_sync(0xffffffffu, rslot, 0);
                 tslot = __shfl_sync(0xffffffffu, tslot, 0);
                 if (rslot >= 0) {
-                    if (NEED_Q) pk_flush<MODE, M4>(W, A, lane, s_table);
+                    if (NEED_Q) pk_flush<MODE, M4>(W, A, lane, lt, s_table);
                     int* r = T.records + (size_t)rslot * PK_REC_WORDS;
                     if (lane == 0) { r[0] = packet; r[1] = (int)subset; r[2] = sp; r[3] = top; r[4] = (int)top_mask; }
                     for (int i = lane; i < sp; i += 32) ((int2*)(r + 8))[i] = W.stack[i];
@@ -564,14 +618,14 @@ trace_packet_kernel(const PkArgs P, const PkTasks T)
                     if (common) pk_leaf_sparse<MODE, M4, true>(W, leaf_mask, n_kept, lane, lt, A, s_table);
                     else pk_leaf_sparse<MODE, M4, false>(W, leaf_mask, n_kept, lane, lt, A, s_table);
                 } else {
-                    if (common) pk_leaf_dense<MODE, M4, true>(W, n_kept, ray, lane, lane_on, A, s_table);
-                    else pk_leaf_dense<MODE, M4, false>(W, n_kept, ray, lane, lane_on, A, s_table);
+                    if (common) pk_leaf_dense<MODE, M4, true>(W, n_kept, ray, lane, lt, lane_on, A, s_table);
+                    else pk_leaf_dense<MODE, M4, false>(W, n_kept, ray, lane, lt, lane_on, A, s_table);
                 }
                 __syncwarp();
             }
         }
         if (suspended) continue;
-        if (NEED_Q) pk_flush<MODE, M4>(W, A, lane, s_table);
+        if (NEED_Q) pk_flush<MODE, M4>(W, A, lane, lt, s_table);
         if (MODE == MODE_COUNT && lane_on) P.out_counts[ray_index] = A.count;
         if (MODE == MODE_CUMULATIVE && lane_on) P.out_cum[ray_index] = A.cum;
         if (P.prof && lane == 0) {
@@ -586,5 +640,5 @@ trace_packet_kernel(const PkArgs P, const PkTasks T)
 template <int MODE, int M4>
 constexpr size_t packet_smem_bytes()
 {
-    return 52 * sizeof(double) + PK_WARPS * sizeof(PkWarp<MODE, M4>);
+    return 52 * sizeof(double2) + PK_WARPS * sizeof(PkWarp<MODE, M4>);
 }
