@@ -172,7 +172,7 @@ def set_trace_mode(mode):
     """'packet' (default), 'ray' (per-ray traversal) or 'packet_ref' (the reference's
     schedule and slab arithmetic bit for bit); see include/grace_b200.h."""
     _check(_sig("grace_b200_set_trace_mode", [_P, _c.c_int])(
-        context(), {"ray": 0, "packet": 1, "packet_ref": 2}[mode]))
+        context(), {"ray": 0, "packet": 1, "packet_ref": 2, "packet_wide": 3}[mode]))
 
 
 def set_trace_budget(steps):

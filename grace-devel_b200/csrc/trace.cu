@@ -424,7 +424,12 @@ int launch_packet(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, int n_packe
 {
     if (MODE == MODE_STATS || MODE == MODE_RAYCOST) return GRACE_B200_EINVAL;   // other kernels
     constexpr int KMODE = (MODE == MODE_STATS || MODE == MODE_RAYCOST) ? MODE_COUNT : MODE;
-    auto kernel = trace_packet_kernel<KMODE, M4>;
+    // the per-packet profile counters exist only in a separate MODE_COUNT instantiation
+    const bool wide = ctx->trace_mode == GRACE_B200_TRACE_PACKET_WIDE;
+    auto kernel = (KMODE == MODE_COUNT && d_prof)
+                      ? (wide ? trace_packet_kernel<KMODE, M4, KMODE == MODE_COUNT, true>
+                              : trace_packet_kernel<KMODE, M4, KMODE == MODE_COUNT, false>)
+                      : (wide ? trace_packet_kernel<KMODE, M4, false, true> : trace_packet_kernel<KMODE, M4, false, false>);
     constexpr size_t psmem = packet_smem_bytes<KMODE, M4>();
     GB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
     int per_sm = 0;
@@ -517,7 +522,8 @@ int launch_trace(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, size_t n_ray
         GB_LAUNCH_CHECK();
         return GRACE_B200_OK;
     }
-    if (MODE != MODE_STATS && MODE != MODE_RAYCOST && ctx->trace_mode == GRACE_B200_TRACE_PACKET &&
+    if (MODE != MODE_STATS && MODE != MODE_RAYCOST &&
+        (ctx->trace_mode == GRACE_B200_TRACE_PACKET || ctx->trace_mode == GRACE_B200_TRACE_PACKET_WIDE) &&
         tree->max_per_leaf <= 128) {
         if (tree->max_per_leaf <= 32)
             return launch_packet<MODE, 32>(ctx, d_rays, n_packets, d_spheres4, tree, out_counts, out_cum,
@@ -572,7 +578,7 @@ int grace_b200_set_trace_budget(grace_b200_ctx* ctx, int steps)
 int grace_b200_set_trace_mode(grace_b200_ctx* ctx, int mode)
 {
     GB_REQUIRE(ctx, GRACE_B200_EINVAL, "ctx is NULL");
-    GB_REQUIRE(mode == GRACE_B200_TRACE_PER_RAY || mode == GRACE_B200_TRACE_PACKET || mode == GRACE_B200_TRACE_PACKET_REF, GRACE_B200_EINVAL,
+    GB_REQUIRE(mode == GRACE_B200_TRACE_PER_RAY || mode == GRACE_B200_TRACE_PACKET || mode == GRACE_B200_TRACE_PACKET_REF || mode == GRACE_B200_TRACE_PACKET_WIDE, GRACE_B200_EINVAL,
                "unknown trace mode %d", mode);
     ctx->trace_mode = mode;
     return GRACE_B200_OK;
@@ -632,7 +638,7 @@ int grace_b200_trace_packet_profile_f4(grace_b200_ctx* ctx, const grace_b200_ray
     if (!d_prof) return GRACE_B200_ENOMEM;
     GB_CUDA(cudaMemsetAsync(d_prof, 0, prof_words * 8, st));
     const int saved = ctx->trace_mode;
-    ctx->trace_mode = GRACE_B200_TRACE_PACKET;
+    if (saved != GRACE_B200_TRACE_PACKET_WIDE) ctx->trace_mode = GRACE_B200_TRACE_PACKET;
     int rc = launch_trace<MODE_COUNT>(ctx, d_rays, n_rays, d_spheres4, n, tree, d_hit_counts, nullptr,
                                       nullptr, nullptr, nullptr, nullptr, st, d_prof);
     ctx->trace_mode = saved;

@@ -36,13 +36,20 @@
 constexpr int PK_THREADS = 128;
 constexpr int PK_WARPS = PK_THREADS / 32;
 #ifndef PK_MIN_BLOCKS_V
-#define PK_MIN_BLOCKS_V 5
+#define PK_MIN_BLOCKS_V 6
 #endif
-constexpr int PK_MIN_BLOCKS = PK_MIN_BLOCKS_V;   // register budget: 65536 / (5 * 128) = 102
-constexpr int PK_STACK = 96;         // reference STACK_SIZE is 64 (kernel_config.h:13)
+constexpr int PK_MIN_BLOCKS = PK_MIN_BLOCKS_V;   // register budget: 65536 / (6 * 128) = 85
+#ifndef PK_STACK_V
+#define PK_STACK_V 256
+#endif
+constexpr int PK_STACK = PK_STACK_V;  // reference STACK_SIZE is 64 (kernel_config.h:13)
+#ifndef PK_DFS_RESERVE_V
+#define PK_DFS_RESERVE_V 64
+#endif
+constexpr int PK_DFS_RESERVE = PK_DFS_RESERVE_V;   // stack slots the wide traversal never fills with a wide step
 constexpr int PK_QD = 8;             // FIFO depth per lane
 #ifndef PK_BATCH_V
-#define PK_BATCH_V 8
+#define PK_BATCH_V 4
 #endif
 constexpr int PK_BATCH = PK_BATCH_V; // leaves fetched together
 #ifndef PK_ROOM_MIN_V
@@ -182,7 +189,7 @@ __device__ __forceinline__ void pk_room(PkWarp<MODE, M4>& W, PkAcc& A, int lane,
 struct PacketBound {
     float ax, ay, az;       // axis direction (unit)
     float ocx, ocy, ocz;    // a point on the axis (lane 0's origin)
-    float r0, tan_t, t0min;
+    float r0, tan_t, t0min, tfar;
     bool enabled;
 };
 
@@ -220,13 +227,18 @@ __device__ __forceinline__ PacketBound packet_bound(const grace_b200_ray& ray)
     const float qx = wx - t0 * B.ax, qy = wy - t0 * B.ay, qz = wz - t0 * B.az;
     const float perp = sqrtf(qx * qx + qy * qy + qz * qz);
     const float cosl = ray.dx * B.ax + ray.dy * B.ay + ray.dz * B.az;
+    // sine from the perpendicular component, not from 1 - cos^2: a cosine that rounds to 1 still
+    // allows an angle of 3.5e-4 rad
+    const float sx_ = ray.dx - cosl * B.ax, sy_ = ray.dy - cosl * B.ay, sz_ = ray.dz - cosl * B.az;
+    const float sinl = sqrtf(sx_ * sx_ + sy_ * sy_ + sz_ * sz_);
     const float cmin = warp_min(cosl);
+    const float smax = warp_max(sinl);
     B.r0 = warp_max(perp) * 1.0001f;
     B.t0min = warp_min(t0);
+    B.tfar = warp_max(t0 + fabsf(ray.length));      // no ray point lies beyond this axial coordinate
     // NaNs (degenerate rays) make the comparisons false -> culling disabled
-    B.enabled = (n2 > 1.0f) && (cmin > 0.5f) && (B.r0 < 1e30f);
-    const float c = fminf(cmin, 1.0f);
-    B.tan_t = sqrtf(fmaxf(1.0f - c * c, 0.0f)) / c * 1.001f + 1e-6f;
+    B.enabled = (n2 > 1e-12f) && (cmin > 0.5f) && (B.r0 < 1e30f) && (B.tfar < 1e30f);
+    B.tan_t = smax / fminf(cmin, 1.0f) * 1.001f + 1e-6f;
     return B;
 }
 
@@ -242,6 +254,44 @@ __device__ __forceinline__ bool packet_may_hit(const PacketBound& B, const float
     const bool outside = d2 > R * R;
     const bool behind = (t + s.w + slack) < B.t0min;
     return !(outside || behind);
+}
+
+// Can any ray of the packet touch the axis-aligned box [b, t]?  Conservative: every point x of
+// the box is at least d - sum_k |qh_k| e_k from the axis (c = centre, e = half extents, q = the
+// perpendicular from the axis to c, d = |q|, qh = q / d), and the packet's radius at the box's
+// farthest axial coordinate bounds its radius everywhere in the box.  Evaluated without the
+// square root: d^2 - sum |q_k| e_k <= R d.
+__device__ __forceinline__ bool packet_may_hit_box(const PacketBound& B, float bx, float tx, float by, float ty,
+                                                   float bz, float tz)
+{
+    const float cx = 0.5f * (bx + tx), cy = 0.5f * (by + ty), cz = 0.5f * (bz + tz);
+    const float ex = 0.5f * (tx - bx), ey = 0.5f * (ty - by), ez = 0.5f * (tz - bz);
+    const float px = cx - B.ocx, py = cy - B.ocy, pz = cz - B.ocz;
+    const float t = px * B.ax + py * B.ay + pz * B.az;
+    const float qx = px - t * B.ax, qy = py - t * B.ay, qz = pz - t * B.az;
+    const float d2 = qx * qx + qy * qy + qz * qz;
+    const float te = fabsf(B.ax) * ex + fabsf(B.ay) * ey + fabsf(B.az) * ez;
+    const float se = fabsf(qx) * ex + fabsf(qy) * ey + fabsf(qz) * ez;
+    const float scale = fabsf(px) + fabsf(py) + fabsf(pz) + ex + ey + ez + B.r0;
+    const float slack = 4e-5f * scale;
+    const float R = B.r0 + fmaxf(0.0f, t + te - B.t0min) * B.tan_t + slack;
+    const float g = d2 - se - slack * scale;         // <= 0: the axis passes within the box's shadow
+    const bool outside = (g > 0.0f) && (g * g > R * R * d2 * 1.0001f);
+    const bool behind = (t + te + slack) < B.t0min;
+    const bool beyond = (t - te - slack) > B.tfar;
+    return !(outside || behind || beyond);            // NaN anywhere -> comparisons false -> kept
+}
+
+// Padded slab test of one ray against one box: t = fma(plane, 1/d, -(o -/+ pad)/d).
+struct PkSlab { float ix, iy, iz, cbx, ctx, cby, cty, cbz, ctz, len; };
+__device__ __forceinline__ bool pk_slab(const PkSlab& S, int bx, int tx, int by, int ty, int bz, int tz)
+{
+    const float a0 = fmaf(__int_as_float(bx), S.ix, S.cbx), a1 = fmaf(__int_as_float(tx), S.ix, S.ctx);
+    const float b0 = fmaf(__int_as_float(by), S.iy, S.cby), b1 = fmaf(__int_as_float(ty), S.iy, S.cty);
+    const float c0 = fmaf(__int_as_float(bz), S.iz, S.cbz), c1 = fmaf(__int_as_float(tz), S.iz, S.ctz);
+    const float tmin = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), 0.0f));
+    const float tmax = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), S.len));
+    return !(tmax < tmin);
 }
 
 // One sphere against one ray: generic/intersect.h:16-48 in the SASS-verified contraction.
@@ -392,7 +442,18 @@ struct PkArgs {
     int* unit_counter; int* err_flag; unsigned long long* prof;
 };
 
-template <int MODE, int M4>
+// Pop the next stack entry that concerns this unit's rays (`subset`); entries whose mask
+// has no ray of the unit are dropped here, so the walk never sees an empty mask.
+#define PK_POP()                                                                         \
+    do {                                                                                 \
+        top = -1;                                                                        \
+        while (sp > 0) {                                                                 \
+            const int2 e_ = W.stack[--sp];                                               \
+            if ((unsigned)e_.y & subset) { top = e_.x; top_mask = (unsigned)e_.y & subset; break; } \
+        }                                                                                \
+    } while (0)
+
+template <int MODE, int M4, bool PROF, bool WIDE>
 __global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS)
 trace_packet_kernel(const PkArgs P, const PkTasks T)
 {
@@ -438,15 +499,27 @@ trace_packet_kernel(const PkArgs P, const PkTasks T)
         __syncwarp();
         W.rays[2 * lane] = make_float4(ray.dx, ray.dy, ray.dz, ray.ox);
         W.rays[2 * lane + 1] = make_float4(ray.oy, ray.oz, ray.length, 0.f);
-        const float ix = __fdiv_rn(1.0f, ray.dx), iy = __fdiv_rn(1.0f, ray.dy),
-                    iz = __fdiv_rn(1.0f, ray.dz);
+        PkSlab S;
+        S.ix = __fdiv_rn(1.0f, ray.dx); S.iy = __fdiv_rn(1.0f, ray.dy); S.iz = __fdiv_rn(1.0f, ray.dz);
+        S.len = ray.length;
         const float pad = 64.0f * 5.9604645e-8f *
                           (fabsf(ray.ox) + fabsf(ray.oy) + fabsf(ray.oz) + fabsf(ray.length));
         // t_bottom = fma(b, inv, cb), t_top = fma(t, inv, ct) with the box grown by pad
-        const float cbx = -(ray.ox + pad) * ix, ctx = -(ray.ox - pad) * ix;
-        const float cby = -(ray.oy + pad) * iy, cty = -(ray.oy - pad) * iy;
-        const float cbz = -(ray.oz + pad) * iz, ctz = -(ray.oz - pad) * iz;
-        const PacketBound B = packet_bound(ray);
+        S.cbx = -(ray.ox + pad) * S.ix; S.ctx = -(ray.ox - pad) * S.ix;
+        S.cby = -(ray.oy + pad) * S.iy; S.cty = -(ray.oy - pad) * S.iy;
+        S.cbz = -(ray.oz + pad) * S.iz; S.ctz = -(ray.oz - pad) * S.iz;
+        // the packet bound covers the unit's own rays only: lanes outside `subset` stand in
+        // with a copy of one that is inside
+        grace_b200_ray bray = ray;
+        if (subset != 0xffffffffu) {
+            const int src = __ffs(subset) - 1;
+            const float b0 = __shfl_sync(0xffffffffu, ray.dx, src), b1 = __shfl_sync(0xffffffffu, ray.dy, src),
+                        b2 = __shfl_sync(0xffffffffu, ray.dz, src), b3 = __shfl_sync(0xffffffffu, ray.ox, src),
+                        b4 = __shfl_sync(0xffffffffu, ray.oy, src), b5 = __shfl_sync(0xffffffffu, ray.oz, src),
+                        b6 = __shfl_sync(0xffffffffu, ray.length, src);
+            if (!lane_on) { bray.dx = b0; bray.dy = b1; bray.dz = b2; bray.ox = b3; bray.oy = b4; bray.oz = b5; bray.length = b6; }
+        }
+        const PacketBound B = packet_bound(bray);
         // all 32 rays share one origin?  (comparisons AFTER the shuffles in packet_bound:
         // every lane must execute every shuffle)
         const bool common = __all_sync(0xffffffffu, (ray.ox == B.ocx) & (ray.oy == B.ocy) & (ray.oz == B.ocz));
@@ -454,11 +527,17 @@ trace_packet_kernel(const PkArgs P, const PkTasks T)
         A.count = 0; A.cum = 0.0f; A.cursor = 0; A.qn = 0; A.room = PK_QD;
         A.hit_idx = P.hit_idx; A.hit_integral = P.hit_integral; A.hit_dist = P.hit_dist;
         int sp = 0;
-        int top = root;
+        int top = root;                  // !WIDE: top of stack in a register
         unsigned top_mask = 0xffffffffu;
+        if (WIDE && !rec) {              // WIDE: everything lives in the stack, {index, parent link}
+            if (lane == 0) W.stack[0] = make_int2(root, 0);
+            sp = 1;
+        }
         if (rec) {      // resume a suspended traversal for the rays in `subset`
             sp = rec[2]; top = rec[3]; top_mask = (unsigned)rec[4] & subset;
             for (int i = lane; i < sp; i += 32) W.stack[i] = ((const int2*)(rec + 8))[i];
+            __syncwarp();
+            if (!WIDE && top_mask == 0u) PK_POP();
             A.cum = __int_as_float(rec[8 + 2 * PK_STACK + lane]);
             A.count = rec[8 + 2 * PK_STACK + 32 + lane];
             A.cursor = rec[8 + 2 * PK_STACK + 64 + lane];
@@ -468,13 +547,13 @@ trace_packet_kernel(const PkArgs P, const PkTasks T)
         __syncwarp();
 
         unsigned long long pf_nodes = 0, pf_leaves = 0, pf_staged = 0, pf_kept = 0;
-        const long long pf_t0 = P.prof ? clock64() : 0;
+        const long long pf_t0 = PROF ? clock64() : 0;
         const int guard0 = 2 * n_nodes + 8;   // a depth-first walk enters each node at most once
         int guard = guard0;
         bool suspended = false;
         for (;;) {
             // ---- suspend an over-budget traversal and hand its rays to several tasks ----
-            if (T.tasks_out && guard0 - guard >= T.budget && top >= 0) {
+            if (T.tasks_out && guard0 - guard >= T.budget && (WIDE ? sp > 0 : top >= 0)) {
                 const unsigned bmask0 = T.child_width >= 32 ? 0xffffffffu : ((1u << T.child_width) - 1u);
                 unsigned blocks = 0;          // bit b: some ray of lane block b belongs to this unit
                 for (int b = 0; b * T.child_width < 32; ++b)
@@ -512,70 +591,144 @@ trace_packet_kernel(const PkArgs P, const PkTasks T)
                     break;
                 }
             }
-            // ---- phase A: walk inner nodes until PK_BATCH leaves are collected ----
+            // ---- phase A: find the next leaves (at most PK_BATCH, in ascending order) ----
             int nb = 0;
             int b_leaf = 0;               // lane b holds batch entry b
             unsigned b_mask = 0;
-            while (top >= 0 && nb < PK_BATCH) {
-                if (top_mask == 0u) {     // nothing below this entry concerns this unit's rays
-                    if (sp > 0) { const int2 e = W.stack[--sp]; top = e.x; top_mask = (unsigned)e.y & subset; }
-                    else top = -1;
-                    continue;
+            if (WIDE) {
+                // The stack holds the pending subtrees in order, leftmost on top.  While the top is an
+                // inner node, up to 32 entries are popped -- one per lane -- every lane fetches ITS node
+                // and tests both child boxes against the packet bound (one conservative test per box
+                // instead of 32 slab tests), and the surviving children go back in the same order.
+                // Leaves pass through; the run of leaves on top is the next batch.  Which leaves are
+                // visited does not affect results: the per-ray slab test on the leaf's own box (below)
+                // and sphere_test decide.
+                int2 e = make_int2(0, 0);
+                for (;;) {
+                    if (sp == 0) break;
+                    if (--guard < 0) { if (lane == 0) atomicMax(P.err_flag, 2); sp = 0; break; }
+                    const int look = min(sp, PK_BATCH);
+                    e = make_int2(0, 0);
+                    if (lane < look) e = W.stack[sp - 1 - lane];
+                    const unsigned leafm = __ballot_sync(0xffffffffu, lane < look && e.x >= n_nodes);
+                    nb = __ffs(~leafm) - 1;
+                    if (nb > 0) break;
+                    // A wide step pops the top 32 entries and may add one entry per node it expands.
+                    // Only the first `allowed` inner nodes (from the top) are expanded, the rest pass
+                    // through: the last PK_DFS_RESERVE slots are kept for one-node-at-a-time descent.
+                    const int k = min(sp, 32);
+                    if (sp >= PK_STACK) { if (lane == 0) atomicMax(P.err_flag, 1); sp = 0; break; }
+                    if (lane >= look && lane < k) e = W.stack[sp - 1 - lane];
+                    bool inner = lane < k && e.x < n_nodes;
+                    const unsigned innerm = __ballot_sync(0xffffffffu, inner);
+                    const int allowed = max(PK_STACK - PK_DFS_RESERVE - sp, 1);
+                    inner = inner && (__popc(innerm & lt) < allowed);
+                    bool keepL = false, keepR = false;
+                    int4 n0 = make_int4(0, 0, 0, 0);
+                    if (inner) {
+                        const int4* np = nodes + 4 * (size_t)e.x;
+                        n0 = __ldg(np + 0);
+                        if (B.enabled) {
+                            const int4 n1 = __ldg(np + 1);
+                            const int4 n2 = __ldg(np + 2);
+                            const int4 n3 = __ldg(np + 3);
+                            keepL = packet_may_hit_box(B, __int_as_float(n1.x), __int_as_float(n1.y), __int_as_float(n1.z),
+                                                       __int_as_float(n1.w), __int_as_float(n3.x), __int_as_float(n3.y));
+                            keepR = packet_may_hit_box(B, __int_as_float(n2.x), __int_as_float(n2.y), __int_as_float(n2.z),
+                                                       __int_as_float(n2.w), __int_as_float(n3.z), __int_as_float(n3.w));
+                        }
+                    }
+                    if (PROF) pf_nodes += __popc(__ballot_sync(0xffffffffu, inner));
+                    if (!B.enabled) {     // incoherent rays: the reference rule, any ray's slab test
+                        unsigned im = __ballot_sync(0xffffffffu, inner);
+                        while (im) {
+                            const int i = __ffs(im) - 1;
+                            im &= im - 1;
+                            const int4* np = nodes + 4 * (size_t)__shfl_sync(0xffffffffu, e.x, i);
+                            const int4 n1 = __ldg(np + 1);
+                            const int4 n2 = __ldg(np + 2);
+                            const int4 n3 = __ldg(np + 3);
+                            const bool aL = __any_sync(0xffffffffu, lane_on && pk_slab(S, n1.x, n1.y, n1.z, n1.w, n3.x, n3.y));
+                            const bool aR = __any_sync(0xffffffffu, lane_on && pk_slab(S, n2.x, n2.y, n2.z, n2.w, n3.z, n3.w));
+                            if (lane == i) { keepL = aL; keepR = aR; }
+                        }
+                    }
+                    int2 o0 = make_int2(-1, 0), o1 = make_int2(-1, 0);
+                    if (inner) {
+                        if (keepL) o0 = make_int2(n0.x, 2 * e.x);
+                        if (keepR) { if (keepL) o1 = make_int2(n0.y, 2 * e.x + 1); else o0 = make_int2(n0.y, 2 * e.x + 1); }
+                    } else if (lane < k) {
+                        o0 = e;           // leaves, and inner nodes beyond `allowed`, pass through
+                    }
+                    const int cnt = (o0.x >= 0) + (o1.x >= 0);
+                    int incl = cnt;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += t;
+                    }
+                    const int tot = __shfl_sync(0xffffffffu, incl, 31);
+                    const int off = incl - cnt;
+                    __syncwarp();         // every popped entry has been read
+                    const int sp_new = sp - k + tot;
+                    if (o0.x >= 0) W.stack[sp_new - 1 - off] = o0;
+                    if (o1.x >= 0) W.stack[sp_new - 2 - off] = o1;
+                    sp = sp_new;
+                    __syncwarp();
                 }
-                if (--guard < 0) { if (lane == 0) atomicMax(P.err_flag, 2); top = -1; break; }
-                if (top < n_nodes) {
-                    if (P.prof) ++pf_nodes;
-                    const int4* np = nodes + 4 * (size_t)top;
-                    const int4 n0 = __ldg(np + 0);
-                    const int4 n1 = __ldg(np + 1);
-                    const int4 n2 = __ldg(np + 2);
-                    const int4 n3 = __ldg(np + 3);
-                    bool hitL, hitR;
-                    {
-                        const float a0 = fmaf(__int_as_float(n1.x), ix, cbx), a1 = fmaf(__int_as_float(n1.y), ix, ctx);
-                        const float b0 = fmaf(__int_as_float(n1.z), iy, cby), b1 = fmaf(__int_as_float(n1.w), iy, cty);
-                        const float c0 = fmaf(__int_as_float(n3.x), iz, cbz), c1 = fmaf(__int_as_float(n3.y), iz, ctz);
-                        const float tmin = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), 0.0f));
-                        const float tmax = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), ray.length));
-                        hitL = !(tmax < tmin);
+                if (nb > 0) {
+                    sp -= nb;
+                    guard -= nb - 1;
+                    b_leaf = e.x - n_nodes;
+                    // per-ray masks: the slab test on the leaf's own box, read from its parent's record
+                    for (int slot = 0; slot < nb; ++slot) {
+                        const int link = __shfl_sync(0xffffffffu, e.y, slot);
+                        const int4* np = nodes + 4 * (size_t)(link >> 1);
+                        const int4 nxy = __ldg(np + 1 + (link & 1));
+                        const int4 nz = __ldg(np + 3);
+                        const bool hit = lane_on && pk_slab(S, nxy.x, nxy.y, nxy.z, nxy.w, (link & 1) ? nz.z : nz.x,
+                                                            (link & 1) ? nz.w : nz.y);
+                        const unsigned m = __ballot_sync(0xffffffffu, hit);
+                        if (lane == slot) b_mask = m;
                     }
-                    {
-                        const float a0 = fmaf(__int_as_float(n2.x), ix, cbx), a1 = fmaf(__int_as_float(n2.y), ix, ctx);
-                        const float b0 = fmaf(__int_as_float(n2.z), iy, cby), b1 = fmaf(__int_as_float(n2.w), iy, cty);
-                        const float c0 = fmaf(__int_as_float(n3.z), iz, cbz), c1 = fmaf(__int_as_float(n3.w), iz, ctz);
-                        const float tmin = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), 0.0f));
-                        const float tmax = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), ray.length));
-                        hitR = !(tmax < tmin);
-                    }
-                    // a lane that missed an ancestor's box cannot hit anything below it
-                    const unsigned mL = __ballot_sync(0xffffffffu, hitL) & top_mask;
-                    const unsigned mR = __ballot_sync(0xffffffffu, hitR) & top_mask;
-                    if (mL && mR) {
-                        if (sp >= PK_STACK) { if (lane == 0) atomicMax(P.err_flag, 1); top = -1; sp = 0; continue; }
-                        W.stack[sp++] = make_int2(n0.y, (int)mR);
-                        // the right child is needed after the whole left subtree: warm its line
-                        if (lane == 0) prefetch_l1(n0.y < n_nodes ? (const void*)(nodes + 4 * (size_t)n0.y)
-                                                                  : (const void*)(leaves + (n0.y - n_nodes)));
-                        top = n0.x; top_mask = mL;
-                    } else if (mL) {
-                        top = n0.x; top_mask = mL;
-                    } else if (mR) {
-                        top = n0.y; top_mask = mR;
+                }
+            } else {
+                while (top >= 0 && nb < PK_BATCH) {
+                    if (--guard < 0) { if (lane == 0) atomicMax(P.err_flag, 2); top = -1; break; }
+                    if (top < n_nodes) {
+                        if (PROF) ++pf_nodes;
+                        const int4* np = nodes + 4 * (size_t)top;
+                        const int4 n0 = __ldg(np + 0);
+                        const int4 n1 = __ldg(np + 1);
+                        const int4 n2 = __ldg(np + 2);
+                        const int4 n3 = __ldg(np + 3);
+                        const bool hitL = pk_slab(S, n1.x, n1.y, n1.z, n1.w, n3.x, n3.y);
+                        const bool hitR = pk_slab(S, n2.x, n2.y, n2.z, n2.w, n3.z, n3.w);
+                        // a lane that missed an ancestor's box cannot hit anything below it
+                        const unsigned mL = __ballot_sync(0xffffffffu, hitL) & top_mask;
+                        const unsigned mR = __ballot_sync(0xffffffffu, hitR) & top_mask;
+                        if (mL && mR) {
+                            if (sp >= PK_STACK) { if (lane == 0) atomicMax(P.err_flag, 1); top = -1; sp = 0; continue; }
+                            W.stack[sp++] = make_int2(n0.y, (int)mR);
+                            top = n0.x; top_mask = mL;
+                        } else if (mL) {
+                            top = n0.x; top_mask = mL;
+                        } else if (mR) {
+                            top = n0.y; top_mask = mR;
+                        } else {
+                            PK_POP();
+                        }
                     } else {
-                        if (sp > 0) { const int2 e = W.stack[--sp]; top = e.x; top_mask = (unsigned)e.y & subset; }
-                        else top = -1;
+                        if (lane == nb) { b_leaf = top - n_nodes; b_mask = top_mask; }
+                        ++nb;
+                        PK_POP();
                     }
-                } else {
-                    if (lane == nb) { b_leaf = top - n_nodes; b_mask = top_mask; }
-                    ++nb;
-                    if (sp > 0) { const int2 e = W.stack[--sp]; top = e.x; top_mask = (unsigned)e.y & subset; }
-                    else top = -1;
                 }
             }
             if (nb == 0) break;
             // ---- phase B: all leaf records in one round trip, then all spheres in one ----
             int2 lf = make_int2(0, 0);
-            if (lane < nb) lf = __ldg((const int2*)(leaves + b_leaf));
+            if (lane < nb && b_mask) lf = __ldg((const int2*)(leaves + b_leaf));
             for (int slot = 0; slot < nb; ++slot) {
                 const int first = __shfl_sync(0xffffffffu, lf.x, slot);
                 const int cnt = min(__shfl_sync(0xffffffffu, lf.y, slot), M4);
@@ -589,6 +742,7 @@ trace_packet_kernel(const PkArgs P, const PkTasks T)
                 const int first = __shfl_sync(0xffffffffu, lf.x, slot);
                 const int cnt = min(__shfl_sync(0xffffffffu, lf.y, slot), M4);
                 const unsigned leaf_mask = __shfl_sync(0xffffffffu, b_mask, slot);
+                if (leaf_mask == 0u) continue;
                 int n_kept = 0;
                 for (int base = 0; base < cnt; base += 32) {
                     const int i = base + lane;
@@ -612,7 +766,7 @@ trace_packet_kernel(const PkArgs P, const PkTasks T)
                     n_kept += __popc(m);
                 }
                 __syncwarp();
-                if (P.prof) { ++pf_leaves; pf_staged += cnt; pf_kept += n_kept; }
+                if (PROF) { ++pf_leaves; pf_staged += cnt; pf_kept += n_kept; }
                 const int k_active = __popc(leaf_mask);
                 if (3 * k_active < 2 * n_kept) {
                     if (common) pk_leaf_sparse<MODE, M4, true>(W, leaf_mask, n_kept, lane, lt, A, s_table);
@@ -628,7 +782,7 @@ trace_packet_kernel(const PkArgs P, const PkTasks T)
         if (NEED_Q) pk_flush<MODE, M4>(W, A, lane, lt, s_table);
         if (MODE == MODE_COUNT && lane_on) P.out_counts[ray_index] = A.count;
         if (MODE == MODE_CUMULATIVE && lane_on) P.out_cum[ray_index] = A.cum;
-        if (P.prof && lane == 0) {
+        if (PROF && lane == 0) {
             atomicAdd(P.prof + 0, pf_nodes); atomicAdd(P.prof + 1, pf_leaves);
             atomicAdd(P.prof + 2, pf_staged); atomicAdd(P.prof + 3, pf_kept);
             unsigned long long* pp = P.prof + 4 + 4 * (size_t)packet;   // per-packet record

@@ -151,17 +151,21 @@ typedef struct {
     int max_per_leaf;
 } grace_b200_tree;
 
-/* Traversal schedule (all three return identical results wherever the reference passes
+/* Traversal schedule (all four return identical results wherever the reference passes
  * its own brute-force test, tests/tree_traversal/tree_traversal.cu:84-121).
  *  PACKET (default): 32 consecutive rays share one traversal as in the reference
  *     (cuda/kernels/bintree_trace.cuh:119-193), with a conservatively padded slab test,
  *     staged leaves and deferred on-hit work; the hit set is exactly the brute-force set.
+ *  PACKET_WIDE: the same leaf work, but inner nodes are culled against a conservative bound
+ *     of the whole packet, 32 nodes at a time (one per lane), instead of one node per step
+ *     with 32 slab tests; per-ray slab tests are made on leaf boxes only.
  *  PER_RAY: every lane walks the tree for its own ray (padded slab test).
  *  PACKET_REF: the reference's schedule and slab arithmetic bit for bit; defines the
  *     traversal counters of grace_b200_trace_stats_f4. */
 #define GRACE_B200_TRACE_PER_RAY    0
 #define GRACE_B200_TRACE_PACKET     1
 #define GRACE_B200_TRACE_PACKET_REF 2
+#define GRACE_B200_TRACE_PACKET_WIDE 3
 int grace_b200_set_trace_mode(grace_b200_ctx* ctx, int mode);
 /* Load balancing of the PACKET schedule: a packet whose traversal exceeds `steps` inner-node
  * + leaf visits is suspended and resumed as several tasks over disjoint subsets of its rays

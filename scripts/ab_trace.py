@@ -26,7 +26,10 @@ def timeit(fn, reps=5):
         ts.append(a.elapsed_time(b))
     return sum(ts) / len(ts)
 
-res = {"lib": os.environ.get("GRACE_B200_LIB", "default")}
+mode = os.environ.get("AB_MODE", "packet")
+gb.set_trace_mode(mode)
+if os.environ.get("AB_BUDGET"): gb.set_trace_budget(int(os.environ["AB_BUDGET"]))
+res = {"lib": os.environ.get("GRACE_B200_LIB", "default").split("_")[-1], "mode": mode, "budget": os.environ.get("AB_BUDGET")}
 res["hitcounts_ms"] = timeit(lambda: gb.trace_hitcounts_sph(rays, s, tree, counts))
 res["cumulative_ms"] = timeit(lambda: gb.trace_cumulative_sph(rays, s, tree, out))
 res["counts_sha"] = hashlib.sha1(counts.cpu().numpy().tobytes()).hexdigest()[:12]

@@ -188,7 +188,7 @@ def test_tree_tiny_and_errors(gb, orc):
 
 
 # ----------------------------------------------------------------------------- trace
-@pytest.fixture(params=["packet", "ray", "packet_ref"], autouse=True)
+@pytest.fixture(params=["packet", "packet_wide", "ray", "packet_ref"], autouse=True)
 def trace_mode(request, gb):
     """Every test below runs under both traversal schedules."""
     gb.set_trace_mode(request.param)
@@ -270,7 +270,7 @@ def test_hit_lists_and_sort(gb, orc, scene):
 def test_packet_splitting_is_exact(gb, orc, scene, budget, trace_mode):
     """Over-budget packets are suspended and resumed as ray-subset tasks; with a tiny
     budget nearly every packet goes through all four rounds.  Results must not change."""
-    if trace_mode != "packet":
+    if trace_mode not in ("packet", "packet_wide"):
         pytest.skip("splitting exists only in the production packet schedule")
     d_s, tree, hs, htree, rays = scene
     gb.set_trace_budget(budget)
