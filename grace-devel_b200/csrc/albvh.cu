@@ -30,6 +30,8 @@
 
 #include <math_constants.h>
 
+#include <algorithm>
+
 namespace {
 
 constexpr int LV_THREADS = 256;
@@ -97,6 +99,18 @@ deltas_xor_kernel(const KeyT* __restrict__ keys, size_t n, KeyT* __restrict__ de
 // ---------------------------------------------------------------------------
 // d(k) = deltas_shifted[k + 1] is the delta between primitives k and k+1, valid for
 // k in [-1, n-1]; d(-1) and d(n-1) are the sentinels.
+//
+// One block handles LV_TILE consecutive nodes, LV_ITEMS consecutive nodes per thread, so a
+// thread's (0..2 per node) leaves are contiguous in the output and one block-wide scan of the
+// per-thread totals orders them.  The tile's running offset comes from a decoupled look-back
+// in which a whole warp inspects 32 predecessor tiles per step.
+constexpr int LV_ITEMS = 8;
+constexpr int LV_TILE = LV_THREADS * LV_ITEMS;
+
+// window index -> shared-memory index: one pad word per 32 keeps the LV_ITEMS-strided
+// accesses of a warp on distinct banks
+__device__ __forceinline__ int lv_sw(int i) { return i + (i >> 5); }
+
 template <typename T, bool STAGED>
 __global__ void __launch_bounds__(LV_THREADS)
 leaves_kernel(const T* __restrict__ deltas_shifted, int n, int mpl,
@@ -111,45 +125,51 @@ leaves_kernel(const T* __restrict__ deltas_shifted, int n, int mpl,
     __shared__ unsigned long long s_excl;
 
     const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_bid = atomicAdd(ticket, 1u);
     __syncthreads();
     const unsigned bid = s_bid;
     const int n_nodes = n - 1;
-    const int j0 = (int)bid * LV_THREADS;
+    const int j0 = (int)bid * LV_TILE;
     const int pad = mpl + 2;
-    // window covers k in [j0 - pad, j0 + LV_THREADS + pad)
+    // window covers k in [j0 - pad, j0 + LV_TILE + pad)
     const int wlo = j0 - pad;
     if (STAGED) {
-        const int wn = LV_THREADS + 2 * pad;
+        const int wn = LV_TILE + 2 * pad;
         for (int i = tid; i < wn; i += LV_THREADS) {
             int k = wlo + i;
             k = max(k, -1);
             k = min(k, n - 1);
-            win[i] = deltas_shifted[k + 1];
+            win[lv_sw(i)] = deltas_shifted[k + 1];
         }
         __syncthreads();
     }
     auto d = [&](int k) -> T {
-        if (STAGED) return win[k - wlo];
+        if (STAGED) return win[lv_sw(k - wlo)];
         return deltas_shifted[k + 1];
     };
 
-    const int j = j0 + tid;
+    // per node: l, r of its subtree (capped scans) and which children are leaves
+    int lo[LV_ITEMS], hi[LV_ITEMS];
+    unsigned emit_bits = 0;           // bit 2i: left child of node i is a leaf, bit 2i+1: right child
     int emit = 0;
-    int l = j, r = j + 1;
-    bool emitL = false, emitR = false;
-    if (j < n_nodes) {
-        const T dj = d(j);
-        while (l > 0 && (j - l + 1) <= mpl && d(l - 1) < dj) --l;
-        while (r < n - 1 && (r - j) <= mpl && !(dj < d(r))) ++r;
-        const int left_size = j - l + 1, right_size = r - j;
-        const bool big = left_size + right_size > mpl;   // sizes are capped at mpl+1
-        emitL = big && left_size <= mpl;
-        emitR = big && right_size <= mpl;
-        emit = (int)emitL + (int)emitR;
+#pragma unroll
+    for (int i = 0; i < LV_ITEMS; ++i) {
+        const int j = j0 + tid * LV_ITEMS + i;
+        int l = j, r = j + 1;
+        if (j < n_nodes) {
+            const T dj = d(j);
+            while (l > 0 && (j - l + 1) <= mpl && d(l - 1) < dj) --l;
+            while (r < n - 1 && (r - j) <= mpl && !(dj < d(r))) ++r;
+            const int left_size = j - l + 1, right_size = r - j;
+            const bool big = left_size + right_size > mpl;   // sizes are capped at mpl+1
+            const bool eL = big && left_size <= mpl, eR = big && right_size <= mpl;
+            emit_bits |= ((unsigned)eL << (2 * i)) | ((unsigned)eR << (2 * i + 1));
+            emit += (int)eL + (int)eR;
+        }
+        lo[i] = l; hi[i] = r;
     }
     // block-wide exclusive scan of emit
-    const int lane = tid & 31, warp = tid >> 5;
     unsigned incl = emit;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -166,40 +186,54 @@ leaves_kernel(const T* __restrict__ deltas_shifted, int n, int mpl,
     }
     const unsigned local_excl = add + incl - emit;
 
-    if (tid == 0) {
+    if (warp == 0) {
         unsigned long long excl = 0;
         if (bid == 0) {
-            gb_st_volatile_u64(block_state, (unsigned long long)block_total | ST_INCL);
+            if (lane == 0) gb_st_volatile_u64(block_state, (unsigned long long)block_total | ST_INCL);
         } else {
-            gb_st_volatile_u64(block_state + bid, (unsigned long long)block_total | ST_AGG);
-            int t = (int)bid - 1;
+            if (lane == 0) gb_st_volatile_u64(block_state + bid, (unsigned long long)block_total | ST_AGG);
+            int t = (int)bid - 1;           // nearest predecessor not yet accounted for
             for (;;) {
-                const unsigned long long v = gb_ld_volatile_u64(block_state + t);
-                const unsigned long long f = v & ST_MASK;
-                if (f == 0) continue;
-                excl += v & ~ST_MASK;
-                if (f == ST_INCL) break;
-                --t;
+                const int idx = t - lane;
+                unsigned long long v = ST_INCL;      // tiles before the first contribute 0
+                if (idx >= 0) {
+                    do { v = gb_ld_volatile_u64(block_state + idx); } while ((v & ST_MASK) == 0);
+                }
+                const unsigned im = __ballot_sync(0xffffffffu, (v & ST_MASK) == ST_INCL);
+                const int first = im ? __ffs(im) - 1 : 32;       // nearest tile with an inclusive prefix
+                unsigned long long c = lane <= first ? (v & ~ST_MASK) : 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                excl += c;
+                if (im) break;
+                t -= 32;
             }
-            gb_st_volatile_u64(block_state + bid, (excl + block_total) | ST_INCL);
+            if (lane == 0) gb_st_volatile_u64(block_state + bid, (excl + block_total) | ST_INCL);
         }
-        s_excl = excl;
-        if ((int)bid == (n_nodes - 1) / LV_THREADS) *n_leaves_out = (int)(excl + block_total);
-        if (bid == 0) leaf_deltas_shifted[0] = deltas_shifted[0];
+        if (lane == 0) {
+            s_excl = excl;
+            if ((int)bid == (n_nodes - 1) / LV_TILE) *n_leaves_out = (int)(excl + block_total);
+            if (bid == 0) leaf_deltas_shifted[0] = deltas_shifted[0];
+        }
     }
     __syncthreads();
     if (emit) {
         unsigned g = (unsigned)s_excl + local_excl;
-        if (emitL) {
-            leaves[g] = make_int4(l, j - l + 1, 0, 0);
-            leaf_deltas_shifted[g + 1] = d(j);          // delta after the leaf's last primitive
-            node_flags[g] = 0u;
-            ++g;
-        }
-        if (emitR) {
-            leaves[g] = make_int4(j + 1, r - j, 0, 0);
-            leaf_deltas_shifted[g + 1] = d(r);
-            node_flags[g] = 0u;
+#pragma unroll
+        for (int i = 0; i < LV_ITEMS; ++i) {
+            const int j = j0 + tid * LV_ITEMS + i;
+            if (emit_bits & (1u << (2 * i))) {
+                leaves[g] = make_int4(lo[i], j - lo[i] + 1, 0, 0);
+                leaf_deltas_shifted[g + 1] = d(j);          // delta after the leaf's last primitive
+                node_flags[g] = 0u;
+                ++g;
+            }
+            if (emit_bits & (1u << (2 * i + 1))) {
+                leaves[g] = make_int4(j + 1, hi[i] - j, 0, 0);
+                leaf_deltas_shifted[g + 1] = d(hi[i]);
+                node_flags[g] = 0u;
+                ++g;
+            }
         }
     }
 }
@@ -207,8 +241,14 @@ leaves_kernel(const T* __restrict__ deltas_shifted, int n, int mpl,
 // ---------------------------------------------------------------------------
 // nodes
 // ---------------------------------------------------------------------------
+// A warp owns 32 consecutive leaves.  (1) Leaf AABBs: 8 lanes per leaf over coalesced sphere
+// loads.  (2) Every node whose whole range lies inside the warp's 32 leaves is built in
+// registers: lane (l - w) holds the finished subtree [l, r]; in each round a left child
+// fetches its right sibling's state by shuffle when that sibling is finished too, writes the
+// parent's complete 64-byte record (the reference layout, cuda/nodes.h:21-36) and becomes the
+// parent.  No atomics, no fences: ~90 % of the nodes.  (3) The subtrees left over climb the
+// Karras/Apetrei way through one arrival counter per node.
 constexpr int ND_THREADS = 256;
-constexpr int ND_GROUP = 8;   // lanes cooperating on one leaf's AABB
 
 template <typename T>
 __global__ void __launch_bounds__(ND_THREADS)
@@ -219,75 +259,131 @@ nodes_kernel(const float4* __restrict__ spheres, const int4* __restrict__ leaves
     const int L = *n_leaves_ptr;
     const int n_nodes = L - 1;
     const int lane = threadIdx.x & 31;
-    const int sub = lane & (ND_GROUP - 1);
-    const int groups_per_block = ND_THREADS / ND_GROUP;
-    const int group = threadIdx.x / ND_GROUP;
-    const int total_groups = gridDim.x * groups_per_block;
-    const int warp_first_group = (threadIdx.x & ~31) / ND_GROUP;
+    const int warps_total = gridDim.x * (ND_THREADS / 32);
+    // w = first leaf of the warp's window
+    for (int w = (blockIdx.x * (ND_THREADS / 32) + (threadIdx.x >> 5)) * 32; w < L; w += warps_total * 32) {
+    const int leaf = w + lane;
+    bool active = leaf < L;
 
-    for (int base = blockIdx.x * groups_per_block + warp_first_group; base < L; base += total_groups) {
-        const int leaf = base + (group - warp_first_group);
-        const bool active = leaf < L;
-        float bx = CUDART_INF_F, by = CUDART_INF_F, bz = CUDART_INF_F;
-        float tx = -CUDART_INF_F, ty = -CUDART_INF_F, tz = -CUDART_INF_F;
-        if (active) {
-            const int4 lf = __ldg(leaves + leaf);
-            for (int i = sub; i < lf.y; i += ND_GROUP) {
-                const float4 s = __ldg(spheres + lf.x + i);
+    // ---- (1) leaf boxes ----
+    int2 lf = make_int2(0, 0);
+    if (active) lf = __ldg((const int2*)(leaves + leaf));
+    float bx = CUDART_INF_F, by = CUDART_INF_F, bz = CUDART_INF_F;
+    float tx = -CUDART_INF_F, ty = -CUDART_INF_F, tz = -CUDART_INF_F;
+    {
+        const int sub = lane & 7, grp = lane >> 3;
+#pragma unroll 2
+        for (int p = 0; p < 8; ++p) {
+            const int src = p * 4 + grp;                    // leaf (within the warp) this group works on
+            const int first = __shfl_sync(0xffffffffu, lf.x, src);
+            const int cnt = __shfl_sync(0xffffffffu, lf.y, src);
+            float ax = CUDART_INF_F, ay = CUDART_INF_F, az = CUDART_INF_F;
+            float cx = -CUDART_INF_F, cy = -CUDART_INF_F, cz = -CUDART_INF_F;
+            for (int i = sub; i < cnt; i += 8) {
+                const float4 s = __ldg(spheres + first + i);
                 // AABBSphere, generic/functors/aabb.h:9-26: centre -/+ h, one FADD each
-                bx = fminf(bx, __fsub_rn(s.x, s.w)); tx = fmaxf(tx, __fadd_rn(s.x, s.w));
-                by = fminf(by, __fsub_rn(s.y, s.w)); ty = fmaxf(ty, __fadd_rn(s.y, s.w));
-                bz = fminf(bz, __fsub_rn(s.z, s.w)); tz = fmaxf(tz, __fadd_rn(s.z, s.w));
+                ax = fminf(ax, __fsub_rn(s.x, s.w)); cx = fmaxf(cx, __fadd_rn(s.x, s.w));
+                ay = fminf(ay, __fsub_rn(s.y, s.w)); cy = fmaxf(cy, __fadd_rn(s.y, s.w));
+                az = fminf(az, __fsub_rn(s.z, s.w)); cz = fmaxf(cz, __fadd_rn(s.z, s.w));
             }
-        }
 #pragma unroll
-        for (int o = 1; o < ND_GROUP; o <<= 1) {
-            bx = fminf(bx, __shfl_xor_sync(0xffffffffu, bx, o));
-            by = fminf(by, __shfl_xor_sync(0xffffffffu, by, o));
-            bz = fminf(bz, __shfl_xor_sync(0xffffffffu, bz, o));
-            tx = fmaxf(tx, __shfl_xor_sync(0xffffffffu, tx, o));
-            ty = fmaxf(ty, __shfl_xor_sync(0xffffffffu, ty, o));
-            tz = fmaxf(tz, __shfl_xor_sync(0xffffffffu, tz, o));
-        }
-        if (!active || sub != 0) continue;
-
-        // ---- climb (group leader only) ----
-        int cur = leaf + n_nodes;      // child index >= n_nodes marks a leaf
-        int l = leaf, r = leaf;
-        for (;;) {
-            const T dl = ld_shifted[l];          // delta(l - 1)
-            const T dr = ld_shifted[r + 1];      // delta(r)
-            const bool right_child = dl < dr;
-            const int parent = right_child ? l - 1 : r;
-            if (parent < 0 || parent >= n_nodes) break;   // cur is the root
-            int* node_i = (int*)(nodes + 4 * (size_t)parent);
-            float* node_f = (float*)node_i;
-            if (right_child) {
-                node_i[1] = cur; node_i[3] = r;
-                *(float4*)(node_f + 8) = make_float4(bx, tx, by, ty);
-                *(float2*)(node_f + 14) = make_float2(bz, tz);
-            } else {
-                node_i[0] = cur; node_i[2] = l;
-                *(float4*)(node_f + 4) = make_float4(bx, tx, by, ty);
-                *(float2*)(node_f + 12) = make_float2(bz, tz);
+            for (int o = 1; o < 8; o <<= 1) {
+                ax = fminf(ax, __shfl_xor_sync(0xffffffffu, ax, o));
+                ay = fminf(ay, __shfl_xor_sync(0xffffffffu, ay, o));
+                az = fminf(az, __shfl_xor_sync(0xffffffffu, az, o));
+                cx = fmaxf(cx, __shfl_xor_sync(0xffffffffu, cx, o));
+                cy = fmaxf(cy, __shfl_xor_sync(0xffffffffu, cy, o));
+                cz = fmaxf(cz, __shfl_xor_sync(0xffffffffu, cz, o));
             }
-            __threadfence();
-            if (atomicAdd(flags + parent, 1u) == 0u) break;    // first arrival stops
-            __threadfence();
-            const int4 n0 = gb_ld_cg_i4(nodes + 4 * (size_t)parent + 0);
-            const int4 n1 = gb_ld_cg_i4(nodes + 4 * (size_t)parent + 1);
-            const int4 n2 = gb_ld_cg_i4(nodes + 4 * (size_t)parent + 2);
-            const int4 n3 = gb_ld_cg_i4(nodes + 4 * (size_t)parent + 3);
-            cur = parent;
-            l = n0.z; r = n0.w;
-            bx = fminf(__int_as_float(n1.x), __int_as_float(n2.x));
-            tx = fmaxf(__int_as_float(n1.y), __int_as_float(n2.y));
-            by = fminf(__int_as_float(n1.z), __int_as_float(n2.z));
-            ty = fmaxf(__int_as_float(n1.w), __int_as_float(n2.w));
-            bz = fminf(__int_as_float(n3.x), __int_as_float(n3.z));
-            tz = fmaxf(__int_as_float(n3.y), __int_as_float(n3.w));
-            if (r - l == L - 1) *root = cur;
+            // lane 4p + g takes the box of group g
+            const int from = (lane & 3) << 3;
+            const float v0 = __shfl_sync(0xffffffffu, ax, from), v1 = __shfl_sync(0xffffffffu, ay, from),
+                        v2 = __shfl_sync(0xffffffffu, az, from), v3 = __shfl_sync(0xffffffffu, cx, from),
+                        v4 = __shfl_sync(0xffffffffu, cy, from), v5 = __shfl_sync(0xffffffffu, cz, from);
+            if ((lane >> 2) == p) { bx = v0; by = v1; bz = v2; tx = v3; ty = v4; tz = v5; }
         }
+    }
+
+    // ---- (2) nodes inside the warp's window ----
+    // dlo = delta(w + lane - 1); dtop = delta(w + 31) (needed by subtrees ending at the last leaf)
+    const T dlo = ld_shifted[min(leaf, L)];
+    const T dtop = ld_shifted[min(w + 32, L)];
+    int cur = leaf + n_nodes;          // child index >= n_nodes marks a leaf
+    int l = leaf, r = leaf;
+    bool right_child = false;
+    int parent = -1;
+    for (;;) {
+        // parent rule: [l, r] is the right child of node l-1 if delta(l-1) < delta(r), else the
+        // left child of node r
+        const T dl = __shfl_sync(0xffffffffu, dlo, (l - w) & 31);
+        T dr = __shfl_sync(0xffffffffu, dlo, (r - w + 1) & 31);
+        if (r - w + 1 >= 32) dr = dtop;
+        right_child = dl < dr;
+        parent = right_child ? l - 1 : r;
+        const bool is_root = active && (parent < 0 || parent >= n_nodes);
+        if (is_root) { *root = cur; active = false; }
+        // a left child looks at the lane holding the subtree that starts at r + 1
+        const int sib = r + 1 - w;
+        const bool sib_in = active && !right_child && sib < 32;
+        const int sl = sib_in ? sib : lane;
+        const bool s_active = __shfl_sync(0xffffffffu, (int)active, sl);
+        const bool s_right = __shfl_sync(0xffffffffu, (int)right_child, sl);
+        const int s_parent = __shfl_sync(0xffffffffu, parent, sl);
+        const int s_r = __shfl_sync(0xffffffffu, r, sl);
+        const int s_cur = __shfl_sync(0xffffffffu, cur, sl);
+        const float sbx = __shfl_sync(0xffffffffu, bx, sl), sby = __shfl_sync(0xffffffffu, by, sl),
+                    sbz = __shfl_sync(0xffffffffu, bz, sl), stx = __shfl_sync(0xffffffffu, tx, sl),
+                    sty = __shfl_sync(0xffffffffu, ty, sl), stz = __shfl_sync(0xffffffffu, tz, sl);
+        const bool merge = sib_in && s_active && s_right && s_parent == parent;
+        const unsigned absorbed = __reduce_or_sync(0xffffffffu, merge ? (1u << sib) : 0u);
+        if (absorbed == 0u) break;
+        if (merge) {
+            int4* np = nodes + 4 * (size_t)parent;
+            np[0] = make_int4(cur, s_cur, l, s_r);
+            np[1] = make_int4(__float_as_int(bx), __float_as_int(tx), __float_as_int(by), __float_as_int(ty));
+            np[2] = make_int4(__float_as_int(sbx), __float_as_int(stx), __float_as_int(sby), __float_as_int(sty));
+            np[3] = make_int4(__float_as_int(bz), __float_as_int(tz), __float_as_int(sbz), __float_as_int(stz));
+            cur = parent; r = s_r;
+            bx = fminf(bx, sbx); by = fminf(by, sby); bz = fminf(bz, sbz);
+            tx = fmaxf(tx, stx); ty = fmaxf(ty, sty); tz = fmaxf(tz, stz);
+        }
+        if ((absorbed >> lane) & 1u) active = false;
+    }
+    // ---- (3) climb across warps ----
+    while (active) {
+        // parent / right_child are current for [l, r] on entry
+        if (parent < 0 || parent >= n_nodes) { *root = cur; break; }
+        int* node_i = (int*)(nodes + 4 * (size_t)parent);
+        float* node_f = (float*)node_i;
+        if (right_child) {
+            node_i[1] = cur; node_i[3] = r;
+            *(float4*)(node_f + 8) = make_float4(bx, tx, by, ty);
+            *(float2*)(node_f + 14) = make_float2(bz, tz);
+        } else {
+            node_i[0] = cur; node_i[2] = l;
+            *(float4*)(node_f + 4) = make_float4(bx, tx, by, ty);
+            *(float2*)(node_f + 12) = make_float2(bz, tz);
+        }
+        __threadfence();
+        if (atomicAdd(flags + parent, 1u) == 0u) break;    // first arrival stops
+        __threadfence();
+        const int4 n0 = gb_ld_cg_i4(nodes + 4 * (size_t)parent + 0);
+        const int4 n1 = gb_ld_cg_i4(nodes + 4 * (size_t)parent + 1);
+        const int4 n2 = gb_ld_cg_i4(nodes + 4 * (size_t)parent + 2);
+        const int4 n3 = gb_ld_cg_i4(nodes + 4 * (size_t)parent + 3);
+        cur = parent;
+        l = n0.z; r = n0.w;
+        bx = fminf(__int_as_float(n1.x), __int_as_float(n2.x));
+        tx = fmaxf(__int_as_float(n1.y), __int_as_float(n2.y));
+        by = fminf(__int_as_float(n1.z), __int_as_float(n2.z));
+        ty = fmaxf(__int_as_float(n1.w), __int_as_float(n2.w));
+        bz = fminf(__int_as_float(n3.x), __int_as_float(n3.z));
+        tz = fmaxf(__int_as_float(n3.y), __int_as_float(n3.w));
+        const T dl = ld_shifted[l];          // delta(l - 1)
+        const T dr = ld_shifted[r + 1];      // delta(r)
+        right_child = dl < dr;
+        parent = right_child ? l - 1 : r;
+    }
     }
 }
 
@@ -305,7 +401,7 @@ int build_typed(grace_b200_ctx* ctx, const float4* d_spheres, size_t n, const T*
                 int mpl, int4* d_nodes, int4* d_leaves, int* d_root, cudaStream_t st)
 {
     const int n_nodes = (int)n - 1;
-    const int lv_blocks = (n_nodes + LV_THREADS - 1) / LV_THREADS;
+    const int lv_blocks = (n_nodes + LV_TILE - 1) / LV_TILE;
     const size_t bytes = gb_align((n + 1) * sizeof(T)) + gb_align(n * sizeof(unsigned)) +
                          gb_align((size_t)lv_blocks * 8) + 256;
     void* ws = gb_workspace(ctx, bytes);
@@ -321,7 +417,9 @@ int build_typed(grace_b200_ctx* ctx, const float4* d_spheres, size_t n, const T*
     GB_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
     const bool staged = mpl <= 2048;
     if (staged) {
-        const size_t smem = (size_t)(LV_THREADS + 2 * (mpl + 2)) * sizeof(T);
+        const size_t wn = (size_t)LV_TILE + 2 * (mpl + 2);
+        const size_t smem = (wn + wn / 32 + 1) * sizeof(T);
+        GB_CUDA(cudaFuncSetAttribute(leaves_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         leaves_kernel<T, true><<<lv_blocks, LV_THREADS, smem, st>>>(
             d_deltas, (int)n, mpl, d_leaves, leaf_deltas, flags, block_state, ticket, d_nleaves);
     } else {
@@ -329,8 +427,9 @@ int build_typed(grace_b200_ctx* ctx, const float4* d_spheres, size_t n, const T*
             d_deltas, (int)n, mpl, d_leaves, leaf_deltas, flags, block_state, ticket, d_nleaves);
     }
     GB_LAUNCH_CHECK();
-    // Upper bound on leaves is n; expected ~ n / (0.6 * mpl).  Grid-stride over groups.
-    const int nd_blocks = grid_cap(ctx, n / 4 + 1, ND_THREADS / ND_GROUP, 8);
+    // The leaf count is only known on the device (anything up to n): warps stride over
+    // 32-leaf windows.
+    const int nd_blocks = grid_cap(ctx, n, ND_THREADS, 8);
     nodes_kernel<T><<<nd_blocks, ND_THREADS, 0, st>>>(d_spheres, d_leaves, d_nleaves, leaf_deltas,
                                                        d_nodes, flags, d_root);
     GB_LAUNCH_CHECK();
