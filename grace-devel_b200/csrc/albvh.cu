@@ -111,7 +111,11 @@ constexpr int LV_TILE = LV_THREADS * LV_ITEMS;
 // accesses of a warp on distinct banks
 __device__ __forceinline__ int lv_sw(int i) { return i + (i >> 5); }
 
-template <typename T, bool STAGED>
+// K > 0: the two bounded scans ("how many consecutive neighbours are smaller") are answered from
+// a sparse table of window maxima, M_k[i] = max d[i .. i + 2^k), by binary descent: K steps per
+// side whatever the data, where the plain scan costs a warp the LONGEST scan among its lanes
+// (close to the cap mpl + 1 for most warps).  2^K > mpl.  K = 0: plain scans (large mpl).
+template <typename T, bool STAGED, int K>
 __global__ void __launch_bounds__(LV_THREADS)
 leaves_kernel(const T* __restrict__ deltas_shifted, int n, int mpl,
               int4* __restrict__ leaves, T* __restrict__ leaf_deltas_shifted,
@@ -134,8 +138,9 @@ leaves_kernel(const T* __restrict__ deltas_shifted, int n, int mpl,
     const int pad = mpl + 2;
     // window covers k in [j0 - pad, j0 + LV_TILE + pad)
     const int wlo = j0 - pad;
+    const int wn = LV_TILE + 2 * pad;
+    const int wstride = lv_sw(wn) + 1;       // words per table level
     if (STAGED) {
-        const int wn = LV_TILE + 2 * pad;
         for (int i = tid; i < wn; i += LV_THREADS) {
             int k = wlo + i;
             k = max(k, -1);
@@ -143,6 +148,18 @@ leaves_kernel(const T* __restrict__ deltas_shifted, int n, int mpl,
             win[lv_sw(i)] = deltas_shifted[k + 1];
         }
         __syncthreads();
+#pragma unroll
+        for (int k = 1; k < K; ++k) {
+            const T* src = win + (k - 1) * wstride;
+            T* dst = win + k * wstride;
+            const int half = 1 << (k - 1);
+            for (int i = tid; i < wn; i += LV_THREADS) {
+                const T a = src[lv_sw(i)];
+                const T b = src[lv_sw(min(i + half, wn - 1))];
+                dst[lv_sw(i)] = a < b ? b : a;
+            }
+            __syncthreads();
+        }
     }
     auto d = [&](int k) -> T {
         if (STAGED) return win[lv_sw(k - wlo)];
@@ -159,8 +176,30 @@ leaves_kernel(const T* __restrict__ deltas_shifted, int n, int mpl,
         int l = j, r = j + 1;
         if (j < n_nodes) {
             const T dj = d(j);
-            while (l > 0 && (j - l + 1) <= mpl && d(l - 1) < dj) --l;
-            while (r < n - 1 && (r - j) <= mpl && !(dj < d(r))) ++r;
+            if (K > 0) {
+                // left: longest run d(j-1), d(j-2), ... < dj, at most min(mpl, j) long
+                const int capl = min(mpl, j), capr = min(mpl, n - 2 - j);
+                int m = 0;
+                int pos = j - wlo;               // window index one past the run's low end
+#pragma unroll
+                for (int k = K - 1; k >= 0; --k) {
+                    const int step = 1 << k;
+                    if (m + step <= capl && win[k * wstride + lv_sw(pos - step)] < dj) { pos -= step; m += step; }
+                }
+                l = j - m;
+                // right: longest run d(j+1), d(j+2), ... <= dj, at most min(mpl, n-2-j) long
+                m = 0;
+                pos = j + 1 - wlo;
+#pragma unroll
+                for (int k = K - 1; k >= 0; --k) {
+                    const int step = 1 << k;
+                    if (m + step <= capr && !(dj < win[k * wstride + lv_sw(pos)])) { pos += step; m += step; }
+                }
+                r = j + 1 + m;
+            } else {
+                while (l > 0 && (j - l + 1) <= mpl && d(l - 1) < dj) --l;
+                while (r < n - 1 && (r - j) <= mpl && !(dj < d(r))) ++r;
+            }
             const int left_size = j - l + 1, right_size = r - j;
             const bool big = left_size + right_size > mpl;   // sizes are capped at mpl+1
             const bool eL = big && left_size <= mpl, eR = big && right_size <= mpl;
@@ -415,17 +454,23 @@ int build_typed(grace_b200_ctx* ctx, const float4* d_spheres, size_t n, const T*
 
     GB_CUDA(cudaMemsetAsync(block_state, 0, (size_t)lv_blocks * 8, st));
     GB_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
-    const bool staged = mpl <= 2048;
-    if (staged) {
-        const size_t wn = (size_t)LV_TILE + 2 * (mpl + 2);
-        const size_t smem = (wn + wn / 32 + 1) * sizeof(T);
-        GB_CUDA(cudaFuncSetAttribute(leaves_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        leaves_kernel<T, true><<<lv_blocks, LV_THREADS, smem, st>>>(
-            d_deltas, (int)n, mpl, d_leaves, leaf_deltas, flags, block_state, ticket, d_nleaves);
-    } else {
-        leaves_kernel<T, false><<<lv_blocks, LV_THREADS, 0, st>>>(
-            d_deltas, (int)n, mpl, d_leaves, leaf_deltas, flags, block_state, ticket, d_nleaves);
-    }
+    // table levels: 2^K > mpl; the table must fit in shared memory
+    int K = 0;
+    while ((1 << K) <= mpl) ++K;
+    const size_t wn = (size_t)LV_TILE + 2 * (mpl + 2);
+    const size_t level_words = wn + wn / 32 + 2;
+    auto launch = [&](auto kernel, size_t smem) -> int {
+        GB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kernel<<<lv_blocks, LV_THREADS, smem, st>>>(d_deltas, (int)n, mpl, d_leaves, leaf_deltas, flags,
+                                                    block_state, ticket, d_nleaves);
+        return GRACE_B200_OK;
+    };
+    int lrc;
+    if (K <= 6 && sizeof(T) * 6 * level_words <= 112 * 1024) lrc = launch(leaves_kernel<T, true, 6>, sizeof(T) * 6 * level_words);
+    else if (K <= 8 && sizeof(T) * 8 * level_words <= 112 * 1024) lrc = launch(leaves_kernel<T, true, 8>, sizeof(T) * 8 * level_words);
+    else if (mpl <= 2048) lrc = launch(leaves_kernel<T, true, 0>, sizeof(T) * level_words);
+    else lrc = launch(leaves_kernel<T, false, 0>, 0);
+    if (lrc) return lrc;
     GB_LAUNCH_CHECK();
     // The leaf count is only known on the device (anything up to n): warps stride over
     // 32-leaf windows.
