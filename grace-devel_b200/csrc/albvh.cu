@@ -280,8 +280,7 @@ leaves_kernel(const T* __restrict__ deltas_shifted, int n, int mpl,
 // ---------------------------------------------------------------------------
 // nodes
 // ---------------------------------------------------------------------------
-// A warp owns 32 consecutive leaves.  (1) Leaf AABBs: 8 lanes per leaf over coalesced sphere
-// loads.  (2) Every node whose whole range lies inside the warp's 32 leaves is built in
+// A warp owns 32 consecutive leaves.  (1) Leaf AABBs: one lane per leaf.  (2) Every node whose whole range lies inside the warp's 32 leaves is built in
 // registers: lane (l - w) holds the finished subtree [l, r]; in each round a left child
 // fetches its right sibling's state by shuffle when that sibling is finished too, writes the
 // parent's complete 64-byte record (the reference layout, cuda/nodes.h:21-36) and becomes the
@@ -309,38 +308,16 @@ nodes_kernel(const float4* __restrict__ spheres, const int4* __restrict__ leaves
     if (active) lf = __ldg((const int2*)(leaves + leaf));
     float bx = CUDART_INF_F, by = CUDART_INF_F, bz = CUDART_INF_F;
     float tx = -CUDART_INF_F, ty = -CUDART_INF_F, tz = -CUDART_INF_F;
-    {
-        const int sub = lane & 7, grp = lane >> 3;
-#pragma unroll 2
-        for (int p = 0; p < 8; ++p) {
-            const int src = p * 4 + grp;                    // leaf (within the warp) this group works on
-            const int first = __shfl_sync(0xffffffffu, lf.x, src);
-            const int cnt = __shfl_sync(0xffffffffu, lf.y, src);
-            float ax = CUDART_INF_F, ay = CUDART_INF_F, az = CUDART_INF_F;
-            float cx = -CUDART_INF_F, cy = -CUDART_INF_F, cz = -CUDART_INF_F;
-            for (int i = sub; i < cnt; i += 8) {
-                const float4 s = __ldg(spheres + first + i);
-                // AABBSphere, generic/functors/aabb.h:9-26: centre -/+ h, one FADD each
-                ax = fminf(ax, __fsub_rn(s.x, s.w)); cx = fmaxf(cx, __fadd_rn(s.x, s.w));
-                ay = fminf(ay, __fsub_rn(s.y, s.w)); cy = fmaxf(cy, __fadd_rn(s.y, s.w));
-                az = fminf(az, __fsub_rn(s.z, s.w)); cz = fmaxf(cz, __fadd_rn(s.z, s.w));
-            }
-#pragma unroll
-            for (int o = 1; o < 8; o <<= 1) {
-                ax = fminf(ax, __shfl_xor_sync(0xffffffffu, ax, o));
-                ay = fminf(ay, __shfl_xor_sync(0xffffffffu, ay, o));
-                az = fminf(az, __shfl_xor_sync(0xffffffffu, az, o));
-                cx = fmaxf(cx, __shfl_xor_sync(0xffffffffu, cx, o));
-                cy = fmaxf(cy, __shfl_xor_sync(0xffffffffu, cy, o));
-                cz = fmaxf(cz, __shfl_xor_sync(0xffffffffu, cz, o));
-            }
-            // lane 4p + g takes the box of group g
-            const int from = (lane & 3) << 3;
-            const float v0 = __shfl_sync(0xffffffffu, ax, from), v1 = __shfl_sync(0xffffffffu, ay, from),
-                        v2 = __shfl_sync(0xffffffffu, az, from), v3 = __shfl_sync(0xffffffffu, cx, from),
-                        v4 = __shfl_sync(0xffffffffu, cy, from), v5 = __shfl_sync(0xffffffffu, cz, from);
-            if ((lane >> 2) == p) { bx = v0; by = v1; bz = v2; tx = v3; ty = v4; tz = v5; }
-        }
+    // every lane folds its own leaf: the loads of one lane are independent (deep unrolling keeps
+    // several 16-byte loads in flight) and the warp's leaves are contiguous in memory, so all
+    // the lines it touches are consumed in full
+#pragma unroll 4
+    for (int i = 0; i < lf.y; ++i) {
+        const float4 s = __ldg(spheres + lf.x + i);
+        // AABBSphere, generic/functors/aabb.h:9-26: centre -/+ h, one FADD each
+        bx = fminf(bx, __fsub_rn(s.x, s.w)); tx = fmaxf(tx, __fadd_rn(s.x, s.w));
+        by = fminf(by, __fsub_rn(s.y, s.w)); ty = fmaxf(ty, __fadd_rn(s.y, s.w));
+        bz = fminf(bz, __fsub_rn(s.z, s.w)); tz = fmaxf(tz, __fadd_rn(s.z, s.w));
     }
 
     // ---- (2) nodes inside the warp's window ----
