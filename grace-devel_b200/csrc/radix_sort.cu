@@ -82,8 +82,23 @@ digit_scan_kernel(const uint32_t* __restrict__ hist, uint32_t* __restrict__ base
     base[p * GB_RADIX + d] = add + incl - c;
 }
 
+#ifndef OS_MINB
+#define OS_MINB 3
+#endif
+#ifndef OS_NT32
+#define OS_NT32 384
+#endif
+#ifndef OS_IPT32
+#define OS_IPT32 16
+#endif
+#ifndef OS_NT64
+#define OS_NT64 384
+#endif
+#ifndef OS_IPT64
+#define OS_IPT64 12
+#endif
 template <typename KeyT, int NT, int IPT>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, OS_MINB)
 onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                 KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                 uint32_t n, int shift, const uint32_t* __restrict__ base,
@@ -119,13 +134,33 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ v
         const uint32_t idx = warp_base + i * 32 + lane;
         key[i] = idx < n ? keys_in[idx] : ~KeyT(0);
     }
+#ifndef OS_LATE_VALS
+    uint32_t val[IPT];     // issued with the keys: their latency hides behind the ranking
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+        const uint32_t idx = warp_base + i * 32 + lane;
+        val[i] = vals_in ? (idx < n ? vals_in[idx] : 0u) : idx;
+    }
+#endif
     // ---- rank within the warp (stable) ----
     uint32_t* wh = warp_hist + warp * GB_RADIX;
     const unsigned lt = gb_lanemask_lt();
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
         const unsigned d = (unsigned)(key[i] >> shift) & (GB_RADIX - 1);
+#ifdef OS_MATCH
         const unsigned peers = __match_any_sync(0xffffffffu, d);
+#else
+        // lanes holding the same digit, from one ballot per digit bit: MATCH.ANY is a
+        // long-latency instruction and sixteen dependent ones per thread dominated the pass
+        unsigned peers = 0xffffffffu;
+#pragma unroll
+        for (int b = 0; b < GB_RADIX_BITS; ++b) {
+            const bool bit = (d >> b) & 1u;
+            const unsigned m = __ballot_sync(0xffffffffu, bit);
+            peers &= bit ? m : ~m;
+        }
+#endif
         const unsigned lower = __popc(peers & lt);
         uint32_t b = 0;
         if (lower == 0) { b = wh[d]; wh[d] = b + __popc(peers); }
@@ -191,7 +226,11 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ v
         const uint32_t pos = digit_start[d] + wh[d] + rank[i];
         const uint32_t idx = warp_base + i * 32 + lane;
         s_keys[pos] = key[i];
+#ifndef OS_LATE_VALS
+        s_vals[pos] = val[i]; (void)idx;
+#else
         s_vals[pos] = vals_in ? (idx < n ? vals_in[idx] : 0u) : idx;
+#endif
     }
     __syncthreads();
     // ---- write digit runs contiguously ----
@@ -205,8 +244,8 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ v
 }
 
 template <typename KeyT> struct SortCfg;
-template <> struct SortCfg<uint32_t> { static constexpr int NT = 384, IPT = 16; };
-template <> struct SortCfg<uint64_t> { static constexpr int NT = 384, IPT = 12; };
+template <> struct SortCfg<uint32_t> { static constexpr int NT = OS_NT32, IPT = OS_IPT32; };
+template <> struct SortCfg<uint64_t> { static constexpr int NT = OS_NT64, IPT = OS_IPT64; };
 
 template <typename KeyT>
 constexpr size_t onesweep_smem()

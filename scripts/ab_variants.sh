@@ -12,7 +12,7 @@ for spec in "$@"; do
   mkdir -p variants/$name
   for f in csrc/*.cu; do
     b=$(basename $f .cu)
-    if [ "$b" = "trace" ] || [ ! -f build/$b.o ]; then
+    if [ "$b" = "${AB_SRC:-trace}" ] || [ ! -f build/$b.o ]; then
       $NVCC $ARCH -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -I../include -Icsrc --expt-relaxed-constexpr $defs -c $f -o variants/$name/$b.o
     else
       cp build/$b.o variants/$name/$b.o
