@@ -36,4 +36,9 @@ for name, (s, rays, mpl, bits) in cases.items():
 # the reference's random ray generator on this device (148 SMs)
 res, info = refrun.run(uniform_spheres(64, seed=1), "gen:4096:1234:0.5:0.5:0.5:2.0", 32, 30, iters=0, lists=False)
 np.savez_compressed(os.path.join(out, "uniform_random_rays_4096_seed1234_b200.npz"), rays=res["rays"])
+# every ray generator of the reference (deterministic ones are device-independent)
+pts = np.random.default_rng(21).random((1500, 3), dtype=np.float32)
+gens = refrun.run_gens(pts, 2048, 1234, 48, 32)
+np.savez_compressed(os.path.join(out, "ray_generators_ref.npz"), points=pts, n_random=2048, seed=1234,
+                    res_x=48, res_y=32, **gens)
 print("done")

@@ -114,3 +114,57 @@ def test_uniform_random_rays_golden(gb):
     rays = torch.empty((4096, 7), dtype=torch.float32, device="cuda")
     gb.uniform_random_rays(rays, 0.5, 0.5, 0.5, 2.0, 1234)
     assert np.array_equal(g["rays"].view(np.uint32), host(rays).view(np.uint32))
+
+
+# ----------------------------------------------------------------------------- ray generators
+def gen_points(n, seed=21):
+    return np.random.default_rng(seed).random((n, 3), dtype=np.float32)
+
+
+def our_gens(gb, points, n_random, seed, rx, ry):
+    """The product's generators with the parameters oracle/ref_gen_driver.cu hard-codes."""
+    P = refrun.GEN_PARAMS
+    out = {}
+    r = torch.empty((n_random, 7), dtype=torch.float32, device="cuda")
+    gb.uniform_random_rays_single_octant(r, *P["octant_origin"], P["octant_length"], gb.Octants.MPM, seed)
+    out["octant"] = host(r)
+    d_pts = dev(points)
+    for name, st in (("o2m_nosort", gb.RaySortType.NoSort), ("o2m_dirsort", gb.RaySortType.DirectionSort)):
+        out[name] = host(gb.one_to_many_rays(None, *P["o2m_origin"], d_pts, st))
+    out["o2m_endsort_aabb"] = host(gb.one_to_many_rays(None, *P["o2m_origin"], d_pts, gb.RaySortType.EndPointSort,
+                                                       P["o2m_aabb"][0], P["o2m_aabb"][1]))
+    out["plane_parallel"] = host(gb.plane_parallel_random_rays(None, rx, ry, P["pp_base"], P["pp_w"], P["pp_h"],
+                                                               P["pp_length"], seed))
+    out["ortho"] = host(gb.orthographic_projection_rays(None, rx, ry, P["cam_pos"], P["look_at"], P["view_up"],
+                                                        P["ortho_extent"], P["cam_length"]))
+    out["pinhole"] = host(gb.pinhole_camera_rays(None, rx, ry, P["cam_pos"], P["look_at"], P["view_up"],
+                                                 P["pinhole_fovy"], P["cam_length"]))
+    return out
+
+
+@pytest.mark.parametrize("n_pts,n_random,seed,rx,ry", [(5000, 32 * 300, 99, 96, 64), (1 << 16, 1 << 16, 1234, 257, 129)])
+def test_all_ray_generators_bit_exact(gb, n_pts, n_random, seed, rx, ry):
+    """Same device: cuRAND sub-sequences, double-precision normalisation, image-plane arithmetic,
+    direction / end-point keys and the stable sort must give the reference's rays bit for bit."""
+    if not refrun.gens_available():
+        pytest.skip("oracle/_ref/ref_gen_driver not built")
+    pts = gen_points(n_pts)
+    ref = refrun.run_gens(pts, n_random, seed, rx, ry)
+    got = our_gens(gb, pts, n_random, seed, rx, ry)
+    for k in refrun.GEN_NAMES:
+        assert ref[k].shape == got[k].shape, k
+        assert np.array_equal(ref[k].view(np.uint32), got[k].view(np.uint32)), k
+
+
+def test_deterministic_generators_golden(gb):
+    """one_to_many / orthographic / pinhole rays do not depend on the device: golden rays recorded
+    from the reference's CUDA build (tests/golden/make_golden.py) must be reproduced anywhere."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ray_generators_ref.npz"))
+    got = our_gens(gb, g["points"], 64, 5, int(g["res_x"]), int(g["res_y"]))
+    for k in ("o2m_nosort", "o2m_dirsort", "o2m_endsort_aabb", "ortho", "pinhole"):
+        assert np.array_equal(g[k].view(np.uint32), got[k].view(np.uint32)), k
+    if torch.cuda.get_device_properties(0).multi_processor_count == 148:   # cuRAND state count ~ SMs
+        for k in ("octant", "plane_parallel"):
+            got2 = our_gens(gb, g["points"], int(g["n_random"]), int(g["seed"]), int(g["res_x"]), int(g["res_y"]))
+            assert np.array_equal(g[k].view(np.uint32), got2[k].view(np.uint32)), k
