@@ -357,10 +357,11 @@ def ALBVH_sph(d_spheres, d_deltas, d_tree):
     return d_tree
 
 
-def build_tree(spheres, tree, low=None, high=None):
-    """tests/helper/tree.cuh:15-43: 30-bit keys + sort, Euclidean deltas, ALBVH."""
+def build_tree(spheres, tree, low=None, high=None, key_bits=30):
+    """tests/helper/tree.cuh:15-43: 30-bit keys + sort, Euclidean deltas, ALBVH
+    (key_bits=63: the same recipe with morton_keys63_sort_sph)."""
     deltas = torch.empty(spheres.shape[0] + 1, dtype=torch.float32, device=spheres.device)
-    morton_keys30_sort_sph(spheres, low, high)
+    (morton_keys30_sort_sph if key_bits == 30 else morton_keys63_sort_sph)(spheres, low, high)
     euclidean_deltas_sph(spheres, deltas)
     ALBVH_sph(spheres, deltas, tree)
     return tree

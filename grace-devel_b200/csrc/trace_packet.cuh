@@ -282,6 +282,13 @@ __device__ __forceinline__ bool packet_may_hit_box(const PacketBound& B, float b
     return !(outside || behind || beyond);            // NaN anywhere -> comparisons false -> kept
 }
 
+__device__ __forceinline__ float pk_finite_rcp(float d)
+{
+    const float big = 18446744073709551616.0f;      // 2^64
+    const float r = __fdiv_rn(1.0f, d);
+    return fabsf(r) <= big ? r : copysignf(big, d);  // inf and NaN (d = 0, -0, NaN) take the clamp
+}
+
 // Padded slab test of one ray against one box: t = fma(plane, 1/d, -(o -/+ pad)/d).
 struct PkSlab { float ix, iy, iz, cbx, ctx, cby, cty, cbz, ctz, len; };
 __device__ __forceinline__ bool pk_slab(const PkSlab& S, int bx, int tx, int by, int ty, int bz, int tz)
@@ -500,7 +507,10 @@ trace_packet_kernel(const PkArgs P, const PkTasks T)
         W.rays[2 * lane] = make_float4(ray.dx, ray.dy, ray.dz, ray.ox);
         W.rays[2 * lane + 1] = make_float4(ray.oy, ray.oz, ray.length, 0.f);
         PkSlab S;
-        S.ix = __fdiv_rn(1.0f, ray.dx); S.iy = __fdiv_rn(1.0f, ray.dy); S.iz = __fdiv_rn(1.0f, ray.dz);
+        // 1/d, finite: with an infinite reciprocal fma(plane, 1/d, -(o +/- pad)/d) is inf - inf.  For
+        // |d| < 2^-64 the ray is treated as parallel to the slab: t = +/-2^64 (plane - o -/+ pad),
+        // whose sign -- all that matters then -- is decided well inside the padding.
+        S.ix = pk_finite_rcp(ray.dx); S.iy = pk_finite_rcp(ray.dy); S.iz = pk_finite_rcp(ray.dz);
         S.len = ray.length;
         const float pad = 64.0f * 5.9604645e-8f *
                           (fabsf(ray.ox) + fabsf(ray.oy) + fabsf(ray.oz) + fabsf(ray.length));

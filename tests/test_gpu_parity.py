@@ -295,6 +295,30 @@ def test_packet_splitting_is_exact(gb, orc, scene, budget, trace_mode):
         gb.set_trace_budget(2048)
 
 
+def test_axis_aligned_and_degenerate_directions(gb, orc, scene):
+    """Rays with zero direction components (orthographic projections along an axis, -0.0, rays
+    inside a box face plane): 1/d is infinite and the slab arithmetic must not turn into
+    inf - inf.  Counts and column densities equal brute force in every schedule."""
+    from util import ortho_rays_z
+    d_s, tree, hs, htree, _ = scene
+    rays = ortho_rays_z(32, -0.05, 1.05)                       # along -z, origins differ
+    extra = rays[:96].copy()
+    extra[:32, 0] = -0.0                                        # negative zero component
+    extra[32:64, :3] = (1.0, 0.0, 0.0); extra[32:64, 3:6] = (-0.5, 0.5, 0.5)   # along +x, common origin
+    extra[64:96, :3] = (0.0, -1.0, 0.0); extra[64:96, 4] = 1.5; extra[64:96, 5] = hs[1234, 2]
+    rays = np.ascontiguousarray(np.concatenate([rays, extra]))
+    d_rays = dev(rays)
+    cnt = torch.empty(len(rays), dtype=torch.int32, device="cuda")
+    cum = torch.empty(len(rays), dtype=torch.float32, device="cuda")
+    gb.trace_hitcounts_sph(d_rays, d_s, tree, cnt)
+    gb.trace_cumulative_sph(d_rays, d_s, tree, cum)
+    assert gb.device_error() == 0
+    ref = orc.brute_hitcounts(rays, hs)
+    assert ref.sum() > 0
+    assert np.array_equal(host(cnt), ref)
+    assert np.array_equal(host(cum).view(np.uint32), orc.brute_cumulative(rays, hs).view(np.uint32))
+
+
 def test_hit_lists_with_sentinels(gb, orc, scene):
     d_s, tree, hs, htree, rays = scene
     rays = rays[:256]
