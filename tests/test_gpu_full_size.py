@@ -1,0 +1,228 @@
+"""GPU tests at BASELINE.json's FULL sizes (configs 2-5).  The oracle cannot run these sizes
+in seconds, so the checks are size-independent properties of the domain plus exact
+comparisons on samples:
+
+  * sortedness / permutation / idempotence of the Morton sort, structural invariants of the
+    ALBVH (ranges partition, leaves <= max_per_leaf, child boxes are exact unions);
+  * ray independence (a ray's result does not depend on which other rays are traced with it),
+    agreement of all traversal schedules (the reference's packet schedule included),
+    hit-list sums reproduce the column density, sorted lists are sorted;
+  * brute force over ALL spheres on sampled rays by the CPU oracle: bit-exact;
+  * a physical invariant: an orthographic image of column density integrates to the number of
+    particles (every particle's kernel integrates to 1 over the plane).
+"""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+N24 = 1 << 24
+
+
+def sha(t):
+    return hashlib.sha1(t.detach().cpu().numpy().tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def snap24(gb):
+    """2^24 synthetic Gadget-shaped particles and their tree (30-bit keys, max_per_leaf = 32)."""
+    if torch.cuda.get_device_properties(0).total_memory < 40 << 30:
+        pytest.skip("needs a large-memory GPU")
+    raw = gb.synth_gadget_spheres(N24, 1234)
+    s = raw.clone()
+    tree = gb.Tree(N24, 32)
+    gb.build_tree(s, tree)
+    torch.cuda.synchronize()
+    return raw, s, tree
+
+
+def test_config2_sort_properties(gb, snap24):
+    raw, s, tree = snap24
+    keys = torch.empty(N24, dtype=torch.int32, device="cuda")
+    bot, top = gb.min_vec3(raw), gb.max_vec3(raw)
+    gb.morton_keys_sph(s, keys, tuple(float(v) for v in bot.cpu()), tuple(float(v) for v in top.cpu()))
+    k = keys.to(torch.int64) & 0xffffffff
+    assert bool((k[1:] >= k[:-1]).all()), "keys of the sorted particles are not ascending"
+    # a permutation: order-free checksums of the raw bits agree
+    a, b = raw.view(torch.int32).to(torch.int64), s.view(torch.int32).to(torch.int64)
+    assert int(a.sum()) == int(b.sum()) and int((a * a % 1000003).sum()) == int((b * b % 1000003).sum())
+    # idempotent and deterministic: sorting the sorted particles changes nothing, rebuilding
+    # gives the same tree bit for bit
+    again = s.clone()
+    tree2 = gb.Tree(N24, 32)
+    gb.build_tree(again, tree2)
+    assert torch.equal(again.view(torch.int32), s.view(torch.int32))
+    assert tree2.n_leaves == tree.n_leaves
+    assert torch.equal(tree2.nodes, tree.nodes) and torch.equal(tree2.leaves, tree.leaves)
+
+
+def test_config2_tree_invariants(gb, snap24):
+    raw, s, tree = snap24
+    L = tree.n_leaves
+    nn = L - 1
+    leaves = tree.leaves[:L].to(torch.int64)
+    first, count = leaves[:, 0], leaves[:, 1]
+    assert int(count.min()) >= 1 and int(count.max()) <= 32
+    assert int(count.sum()) == N24
+    assert torch.equal(first, torch.cumsum(count, 0) - count), "leaves do not tile the particles in order"
+    nodes = tree.nodes.view(-1, 16)[:nn]
+    left, right = nodes[:, 0].to(torch.int64), nodes[:, 1].to(torch.int64)
+    lo, hi = nodes[:, 2].to(torch.int64), nodes[:, 3].to(torch.int64)
+    root = int(tree.root_index_ptr.item())
+    assert int(lo[root]) == 0 and int(hi[root]) == L - 1
+    # every child index appears exactly once (a tree), ranges of the children partition the parent's
+    seen = torch.zeros(nn + L, dtype=torch.int32, device="cuda")
+    seen.index_add_(0, left, torch.ones_like(left, dtype=torch.int32))
+    seen.index_add_(0, right, torch.ones_like(right, dtype=torch.int32))
+    seen[root] += 1
+    assert bool((seen == 1).all())
+
+    def rng(c):     # [first leaf, last leaf] of child index c
+        inner = c < nn
+        ci = torch.where(inner, c, torch.zeros_like(c))
+        return torch.where(inner, lo[ci], c - nn), torch.where(inner, hi[ci], c - nn)
+    l0, l1 = rng(left)
+    r0, r1 = rng(right)
+    assert torch.equal(l0, lo) and torch.equal(r1, hi) and torch.equal(l1 + 1, r0)
+    # boxes: stored child box == union of that child's own two boxes (inner child) ...
+    f = nodes.view(torch.float32)
+    boxes = {"L": (f[:, 4], f[:, 5], f[:, 6], f[:, 7], f[:, 12], f[:, 13]),
+             "R": (f[:, 8], f[:, 9], f[:, 10], f[:, 11], f[:, 14], f[:, 15])}
+    for side, child in (("L", left), ("R", right)):
+        inner = child < nn
+        c = child[inner]
+        bx, tx, by, ty, bz, tz = (b[inner] for b in boxes[side])
+        for got, a, b_, fn in ((bx, boxes["L"][0], boxes["R"][0], torch.minimum), (tx, boxes["L"][1], boxes["R"][1], torch.maximum),
+                               (by, boxes["L"][2], boxes["R"][2], torch.minimum), (ty, boxes["L"][3], boxes["R"][3], torch.maximum),
+                               (bz, boxes["L"][4], boxes["R"][4], torch.minimum), (tz, boxes["L"][5], boxes["R"][5], torch.maximum)):
+            assert torch.equal(got, fn(a[c], b_[c]))
+    # ... and for leaf children the exact AABB of their spheres (checked on a sample of leaves)
+    sample = torch.arange(0, nn, 997, device="cuda")
+    for side, child in (("L", left), ("R", right)):
+        ch = child[sample]
+        ok = ch >= nn
+        for node, c in zip(sample[ok][:200].tolist(), ch[ok][:200].tolist()):
+            b0, n_ = int(first[c - nn]), int(count[c - nn])
+            sp = s[b0:b0 + n_]
+            want = ((sp[:, 0] - sp[:, 3]).min(), (sp[:, 0] + sp[:, 3]).max(), (sp[:, 1] - sp[:, 3]).min(),
+                    (sp[:, 1] + sp[:, 3]).max(), (sp[:, 2] - sp[:, 3]).min(), (sp[:, 2] + sp[:, 3]).max())
+            got = tuple(b[node] for b in boxes[side])
+            assert all(float(w) == float(g) for w, g in zip(want, got))
+
+
+def test_config3_trace_full_size(gb, orc, snap24):
+    raw, s, tree = snap24
+    r = 1 << 20
+    lo, hi = gb.min_max_x(s)
+    c = (lo + hi) / 2
+    rays = torch.empty((r, 7), dtype=torch.float32, device="cuda")
+    gb.uniform_random_rays(rays, c, c, c, 2 * (hi - lo), 1234)
+    cnt = torch.empty(r, dtype=torch.int32, device="cuda")
+    cum = torch.empty(r, dtype=torch.float32, device="cuda")
+    res = {}
+    try:
+        for mode in ("packet", "packet_wide", "packet_ref"):
+            gb.set_trace_mode(mode)
+            gb.trace_hitcounts_sph(rays, s, tree, cnt)
+            gb.trace_cumulative_sph(rays, s, tree, cum)
+            assert gb.device_error() == 0
+            res[mode] = (sha(cnt), sha(cum))
+    finally:
+        gb.set_trace_mode("packet")
+    assert res["packet"] == res["packet_ref"] == res["packet_wide"], res
+    gb.trace_hitcounts_sph(rays, s, tree, cnt)
+    gb.trace_cumulative_sph(rays, s, tree, cum)
+    # ray independence: every 5th packet traced alone gives the same bits
+    pk = torch.arange(0, r // 32, 5, device="cuda")
+    idx = (pk[:, None] * 32 + torch.arange(32, device="cuda")[None, :]).reshape(-1)
+    sub = rays[idx].contiguous()
+    cnt2 = torch.empty(len(idx), dtype=torch.int32, device="cuda")
+    cum2 = torch.empty(len(idx), dtype=torch.float32, device="cuda")
+    gb.trace_hitcounts_sph(sub, s, tree, cnt2)
+    gb.trace_cumulative_sph(sub, s, tree, cum2)
+    assert torch.equal(cnt2, cnt[idx]) and torch.equal(cum2.view(torch.int32), cum[idx].view(torch.int32))
+    # hit lists on 2^15 rays: counts, sums (1e-5), sortedness after sort_by_distance
+    part = rays[: 1 << 15].contiguous()
+    off = torch.empty(1 << 15, dtype=torch.int32, device="cuda")
+    hidx, integ, dist = gb.trace_sph(part, s, tree, off)
+    ends = torch.cat([off[1:], torch.tensor([hidx.numel()], dtype=torch.int32, device="cuda")])
+    assert torch.equal(ends - off, cnt[: 1 << 15])
+    seg = torch.repeat_interleave(torch.arange(1 << 15, device="cuda"), (ends - off).to(torch.int64))
+    sums = torch.zeros(1 << 15, dtype=torch.float64, device="cuda").index_add_(0, seg, integ.double())
+    want = cum[: 1 << 15].double()
+    assert float(((sums - want).abs() / want.abs().clamp_min(1e-30)).max()) <= 1e-5
+    gb.sort_by_distance(dist, off, hidx, integ)
+    same_seg = seg[1:] == seg[:-1]
+    assert bool((dist[1:][same_seg] >= dist[:-1][same_seg]).all())
+    # brute force over all 2^24 spheres on 64 sampled rays: bit-exact
+    pick = torch.arange(0, r, r // 64, device="cuda")[:64]
+    h_r, h_s = rays[pick].cpu().numpy(), s.cpu().numpy()
+    assert np.array_equal(orc.brute_hitcounts(h_r, h_s), cnt[pick].cpu().numpy())
+    assert np.array_equal(orc.brute_cumulative(h_r, h_s).view(np.uint32), cum[pick].cpu().numpy().view(np.uint32))
+
+
+def test_config4_projection_full_size(gb, orc, snap24):
+    """4096 x 4096 orthographic column-density image (tests/project_gadget/project_gadget.cu:
+    66-80, tests/helper/rays.cuh:55-79) + sorted hit lists on one tile of rays."""
+    raw, s, tree = snap24
+    side = 4096
+    mins = [float(v) for v in gb.min_vec4(s).cpu()]
+    maxs = [float(v) for v in gb.max_vec4(s).cpu()]
+    cx, cy, cz = [(mins[k] + maxs[k]) / 2 for k in range(3)]
+    span = [maxs[k] - mins[k] for k in range(3)]
+    span[0] = span[1] = max(span[0], span[1])
+    rays = gb.orthographic_projection_rays(None, side, side, (cx, cy, span[2]), (cx, cy, cz), (0, 1, 0),
+                                           span[1], 2 * span[2])
+    img = torch.empty(side * side, dtype=torch.float32, device="cuda")
+    gb.trace_cumulative_sph(rays, s, tree, img)
+    assert gb.device_error() == 0
+    # every particle's kernel integrates to 1 over the image plane: sum(image) * pixel area = N
+    # (particles within h of the box faces lose the part of their kernel outside the image)
+    mass = float(img.double().sum()) * (span[0] / side) * (span[1] / side)
+    assert abs(mass / N24 - 1.0) < 5e-3, mass / N24
+    # image rows re-traced with the reference's own packet schedule: same bits
+    rows = torch.tensor([0, 1000, 2048, 4095], device="cuda")
+    idx = (rows[:, None] * side + torch.arange(side, device="cuda")[None, :]).reshape(-1)
+    sub = rays[idx].contiguous()
+    ref = torch.empty(len(idx), dtype=torch.float32, device="cuda")
+    try:
+        gb.set_trace_mode("packet_ref")
+        gb.trace_cumulative_sph(sub, s, tree, ref)
+    finally:
+        gb.set_trace_mode("packet")
+    assert torch.equal(ref.view(torch.int32), img[idx].view(torch.int32))
+    # brute force on 32 pixels
+    pick = torch.arange(0, side * side, side * side // 32, device="cuda")[:32] + 17
+    h_r, h_s = rays[pick].cpu().numpy(), s.cpu().numpy()
+    assert np.array_equal(orc.brute_cumulative(h_r, h_s).view(np.uint32), img[pick].cpu().numpy().view(np.uint32))
+
+
+def test_config5_healpix_2p27(gb, orc):
+    """2^27 particles (63-bit keys), 2^24 HEALPix NESTED rays (nside 2048, pixels [0, 2^24))
+    from the box centre; checked by brute force on sampled rays and against chealpix's
+    published pix2vec_nest restated in the oracle."""
+    if torch.cuda.get_device_properties(0).total_memory < 100 << 30:
+        pytest.skip("needs a large-memory GPU")
+    n = 1 << 27
+    s = gb.synth_gadget_spheres(n, 1234)
+    tree = gb.Tree(n, 32)
+    gb.build_tree(s, tree, key_bits=63)
+    lo, hi = gb.min_max_x(s)
+    c = (lo + hi) / 2
+    r = 1 << 24
+    rays = gb.healpix_rays(None, 2048, 0, r, c, c, c, 2 * (hi - lo))
+    # directions: unit vectors of the NESTED pixel centres
+    pick = torch.arange(0, r, r // 4096, device="cuda")[:4096]
+    v = orc.pix2vec_nest(2048, pick.cpu().numpy())
+    got = rays[pick, :3].cpu().numpy().astype(np.float64)
+    assert np.abs(got - v).max() < 2e-7
+    cum = torch.empty(r, dtype=torch.float32, device="cuda")
+    gb.trace_cumulative_sph(rays, s, tree, cum)
+    assert gb.device_error() == 0
+    assert bool(torch.isfinite(cum).all()) and float(cum.min()) >= 0.0
+    pick = torch.arange(0, r, r // 16, device="cuda")[:16] + 5
+    h_r, h_s = rays[pick].cpu().numpy(), s.cpu().numpy()
+    assert np.array_equal(orc.brute_cumulative(h_r, h_s).view(np.uint32), cum[pick].cpu().numpy().view(np.uint32))
