@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--cpu-sample-rays", type=int, default=0, help="0 = auto (~10-30 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-build-timing", action="store_true")
+    ap.add_argument("--no-reference-cuda", action="store_true",
+                    help="skip timing the reference's own CUDA build (oracle/_ref/ref_driver) beside this run")
     return ap.parse_args()
 
 
@@ -399,6 +401,25 @@ def run_b200(args):
                "parity_bit_exact_vs_oracle": bool(np.array_equal(got[:n_exact].view(np.uint32), exact.view(np.uint32))),
                "parity_rays_checked_bit_exact": n_exact}
 
+    # ---- the reference's own CUDA build on the same box and inputs (a reported baseline) ----
+    ref_cuda = None
+    if not args.no_reference_cuda and world == 1:
+        try:
+            import refrun
+            if refrun.available():
+                h_in = gb.synth_gadget_spheres(n, 1234).cpu().numpy()
+                _, info = refrun.run(h_in, "gen:%d:1234:%.9g:%.9g:%.9g:%.9g" % (r, c, c, c, length),
+                                     args.max_per_leaf, 30, iters=2, lists=False, timeout=600)
+                ref_ms = info["ms_cumulative"]
+                ref_cuda = {"value": r / ref_ms / 1e3, "unit": "Mrays/s", "ms_cumulative": ref_ms,
+                            "ms_hitcounts": info["ms_hitcounts"],
+                            "build_ms": info["ms_keys_sort"] + info["ms_deltas"] + info["ms_albvh"],
+                            "build_mparticles_s": n / (info["ms_keys_sort"] + info["ms_deltas"] + info["ms_albvh"]) / 1e3,
+                            "what": "GRACE's headers (patched only for CUDA-12 API removals, oracle/patch_ref.py) "
+                                    "called through its public API on the same particles and rays, CUDA events"}
+        except Exception as e:      # a baseline, never a reason to lose the bench line
+            ref_cuda = {"unavailable": str(e)[:200]}
+
     line = {
         "metric": "SPH trace Mrays/s (cumulative column density)", "value": value, "unit": "Mrays/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -411,6 +432,7 @@ def run_b200(args):
         "gpu_launches": args.steps * world * 4,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "reference_cuda": ref_cuda,
         "build": build_info,
         "wall_s_timed_region": t_wall,
         "n_leaves": tree.n_leaves,

@@ -30,7 +30,8 @@ __all__ = [
     "min_vec3", "max_vec3", "min_max_x", "min_vec4", "max_vec4",
     "uniform_random_rays", "uniform_random_rays_single_octant", "one_to_many_rays",
     "plane_parallel_random_rays", "orthographic_projection_rays", "pinhole_camera_rays",
-    "healpix_rays", "synth_gadget_spheres", "context", "lib", "build_tree", "set_trace_mode", "set_trace_budget", "device_error", "sharded_trace", "tiles_of_rank",
+    "healpix_rays", "synth_gadget_spheres", "exclusive_segmented_scan",
+    "weighted_exclusive_segmented_scan", "offsets_to_segments", "context", "lib", "build_tree", "set_trace_mode", "set_trace_budget", "device_error", "sharded_trace", "tiles_of_rank",
 ]
 
 _c = ctypes
@@ -91,6 +92,9 @@ _t_hfill = _sig("grace_b200_trace_hits_fill_f4", [_P, _P, _sz, _P, _sz, _TS, _P,
 _t_stats = _sig("grace_b200_trace_stats_f4", [_P, _P, _sz, _P, _sz, _TS, _c.POINTER(_c.c_longlong * 4), _P])
 _sort_dist = _sig("grace_b200_sort_by_distance", [_P, _P, _P, _sz, _sz, _P, _P, _P])
 _scan = _sig("grace_b200_exclusive_scan_i32", [_P, _P, _P, _sz, _P, _P])
+_segscan = _sig("grace_b200_exclusive_segmented_scan_f32", [_P, _P, _sz, _P, _sz, _P, _P])
+_wsegscan = _sig("grace_b200_weighted_exclusive_segmented_scan_f32", [_P, _P, _P, _P, _P, _sz, _sz, _P, _P])
+_off2seg = _sig("grace_b200_offsets_to_segments", [_P, _P, _sz, _P, _sz, _P])
 _table = _sig("grace_b200_kernel_integral_table", [_c.POINTER(_c.c_int)], _c.POINTER(_c.c_double))
 
 
@@ -461,6 +465,41 @@ def sort_by_distance(d_hit_distances, d_ray_offsets, d_hit_indices, d_hit_data):
         raise TypeError("d_hit_data must hold one 32-bit value per hit")
     _check(_sort_dist(context(), _dp(d_hit_distances), _dp(d_ray_offsets), d_ray_offsets.numel(),
                       d_hit_distances.numel(), _dp(d_hit_indices), _dp(d_hit_data), _stream()))
+
+
+def exclusive_segmented_scan(d_segment_offsets, d_data, d_results):
+    """cuda/scan.cuh:15-38.  d_data and d_results may be the same tensor."""
+    _need(d_segment_offsets, torch.int32, "d_segment_offsets")
+    _need(d_data, torch.float32, "d_data")
+    _need(d_results, torch.float32, "d_results")
+    if d_results.numel() != d_data.numel():
+        raise ValueError("d_results must have one value per datum")
+    _check(_segscan(context(), _dp(d_segment_offsets), d_segment_offsets.numel(), _dp(d_data), d_data.numel(),
+                    _dp(d_results), _stream()))
+    return d_results
+
+
+def weighted_exclusive_segmented_scan(d_to_sum, d_weights, d_weight_map, d_segment_offsets, d_sum):
+    """cuda/scan.cuh:45-58: scans d_weights[d_weight_map[i]] * d_to_sum[i]; d_weight_map is
+    uint32 in the reference (int32 tensors hold the same bits)."""
+    _need(d_to_sum, torch.float32, "d_to_sum")
+    _need(d_weights, torch.float32, "d_weights")
+    _need(d_weight_map, torch.int32, "d_weight_map")
+    _need(d_segment_offsets, torch.int32, "d_segment_offsets")
+    _need(d_sum, torch.float32, "d_sum")
+    if d_weight_map.numel() != d_to_sum.numel() or d_sum.numel() != d_to_sum.numel():
+        raise ValueError("d_weight_map and d_sum must have one value per datum")
+    _check(_wsegscan(context(), _dp(d_to_sum), _dp(d_weights), _dp(d_weight_map), _dp(d_segment_offsets),
+                     d_segment_offsets.numel(), d_to_sum.numel(), _dp(d_sum), _stream()))
+    return d_sum
+
+
+def offsets_to_segments(d_offsets, d_segments):
+    """cuda/sort.cuh:20-41."""
+    _need(d_offsets, torch.int32, "d_offsets")
+    _need(d_segments, torch.int32, "d_segments")
+    _check(_off2seg(context(), _dp(d_offsets), d_offsets.numel(), _dp(d_segments), d_segments.numel(), _stream()))
+    return d_segments
 
 
 def exclusive_scan(d_in, d_out=None):

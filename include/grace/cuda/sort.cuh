@@ -17,4 +17,12 @@ GRACE_HOST void sort_by_distance(RealVec& d_hit_distances, const IntVec& d_ray_o
                                                  detail::raw(d_hit_data.data()), nullptr));
 }
 
+// Segment index of every element from per-segment offsets (cuda/sort.cuh:20-41).
+template <typename IntVec>
+GRACE_HOST void offsets_to_segments(const IntVec& d_offsets, IntVec& d_segments)
+{
+    GRACE_B200_CHECK(grace_b200_offsets_to_segments(detail::context(), detail::raw(d_offsets.data()), d_offsets.size(),
+                                                    detail::raw(d_segments.data()), d_segments.size(), nullptr));
+}
+
 } // namespace grace

@@ -293,6 +293,26 @@ int grace_b200_synth_gadget_f4(grace_b200_ctx* ctx, float* d_spheres4, size_t n,
 int grace_b200_exclusive_scan_i32(grace_b200_ctx* ctx, const int* d_in, int* d_out, size_t n,
                                   long long* d_total, void* stream);
 
+/* ---- after the path: scans along sorted hit lists ------------- */
+/* replaces: exclusive_segmented_scan (cuda/scan.cuh:15-38).  d_results[i] = sum of
+ * d_data[segment start .. i); segment s = [offsets[s], offsets[s+1]) and the last one ends at
+ * n_data.  d_data and d_results may be the same array.  Exact for integer-valued data (the
+ * reference's test, tests/segmented_scan/segmented_scan.cu:97-140); general floats are summed
+ * in 32-element warp-scan order, within rounding of the sequential sum. */
+int grace_b200_exclusive_segmented_scan_f32(grace_b200_ctx* ctx, const int* d_segment_offsets,
+                                            size_t n_segments, const float* d_data, size_t n_data,
+                                            float* d_results, void* stream);
+/* replaces: weighted_exclusive_segmented_scan (cuda/scan.cuh:45-58) with multiply_by_weights
+ * (cuda/kernels/weights.cuh:13-59) fused: scans d_weights[d_weight_map[i]] * d_to_sum[i]. */
+int grace_b200_weighted_exclusive_segmented_scan_f32(grace_b200_ctx* ctx, const float* d_to_sum,
+                                                     const float* d_weights, const unsigned* d_weight_map,
+                                                     const int* d_segment_offsets, size_t n_segments,
+                                                     size_t n_data, float* d_sum, void* stream);
+/* replaces: offsets_to_segments (cuda/sort.cuh:20-41), including its numbering when segments
+ * are empty (count of distinct values among offsets[1..s]). */
+int grace_b200_offsets_to_segments(grace_b200_ctx* ctx, const int* d_offsets, size_t n_offsets,
+                                   int* d_segments, size_t n_data, void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

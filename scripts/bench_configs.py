@@ -105,6 +105,12 @@ if 4 in want:
         a.record(); idx, integ, dist = gb.trace_sph(sub, s, tree, off)
         b.record(); gb.sort_by_distance(dist, off, idx, integ)
         c2.record(); torch.cuda.synchronize()
+        if k == 1:   # the step after the path: optical-depth style scan along the sorted lists (8 B/hit)
+            tau = torch.empty_like(integ)
+            t_scan = timed(lambda: gb.exclusive_segmented_scan(off, integ, tau), reps=3)
+            scan_info = dict(hits=idx.numel(), ms=t_scan, ghits_s=idx.numel() / t_scan / 1e6,
+                             hbm_frac=8.0 * idx.numel() / (t_scan * 1e-3) / 1e9 / peak)
+            del tau
         t_lists += a.elapsed_time(b); t_sort += b.elapsed_time(c2); hits += idx.numel()
         if k == 0:   # sortedness + the list reproduces the column density
             o = off.cpu().numpy(); d = dist.cpu().numpy(); ends = np.append(o[1:], len(d))
@@ -118,7 +124,7 @@ if 4 in want:
     out["config4_project_gadget"] = dict(n=n, image=[side, side], gen_rays_ms=t_gen, cumulative_ms=t_cum, mrays_s_cumulative=r / t_cum / 1e3,
         mass_recovered_over_n=mass / n, lists=dict(tiles=n_tiles, rays_per_tile=tile, hits=hits, trace_ms=t_lists, sort_ms=t_sort,
         mrays_s=n_tiles * tile / (t_lists + t_sort) / 1e3, mhits_s=hits / (t_lists + t_sort) / 1e3, sorted=bool(ok_sorted),
-        list_sum_vs_cumulative_max_rel=rel))
+        list_sum_vs_cumulative_max_rel=rel), exclusive_segmented_scan=scan_info)
     del rays, cum
 
 if 5 in want:

@@ -4,16 +4,19 @@
 //   tree_traversal/tree_traversal.cu:46-121       -> test_tree_traversal
 //   integrate/integrate.cu:48-101                 -> test_integrate
 //   distance_sort/distance_sort.cu:22-79,125-148  -> test_distance_sort
+//   segmented_scan/segmented_scan.cu:66-160       -> test_segmented_scan
 // plus the argument-error behaviour (std::invalid_argument).  Plain host C++: the CUDA work
 // happens behind the C ABI in libgrace_b200.so.
 #include "grace/cuda/build_sph.cuh"
 #include "grace/cuda/gen_rays.cuh"
+#include "grace/cuda/scan.cuh"
 #include "grace/cuda/sort.cuh"
 #include "grace/cuda/trace_sph.cuh"
 #include "grace/cuda/util/extrema.cuh"
 #include "grace/generic/intersect.h"
 #include "grace/generic/morton.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -157,6 +160,51 @@ static int test_distance_sort()
     return failures == 0 && !dist.empty() ? 0 : 1;
 }
 
+// tests/segmented_scan/segmented_scan.cu:66-160: random segment sizes (empty ones allowed),
+// integer-valued data in [1, 9], compared element by element with the sequential host scan.
+static int test_segmented_scan(int count, int random_size, bool support_empty)
+{
+    std::vector<int> seg_counts, csr;
+    int total = 0;
+    unsigned k = 12345u + (unsigned)random_size;
+    auto my_rand = [&](int lo, int hi) { k = hash_u32(k); return (int)(k % (unsigned)(hi + 1 - lo)) + lo; };
+    while (total < count) {
+        const int seg = my_rand(support_empty ? 0 : 1, std::min(random_size, count - total));
+        csr.push_back(total ? csr.back() + seg_counts.back() : 0);
+        seg_counts.push_back(seg);
+        total += seg;
+    }
+    const int rows = (int)seg_counts.size();
+    std::vector<float> data(count), weights(37);
+    std::vector<unsigned> map(count);
+    for (int i = 0; i < count; ++i) { data[i] = (float)my_rand(1, 9); map[i] = (unsigned)my_rand(0, 36); }
+    for (int i = 0; i < 37; ++i) weights[i] = (float)my_rand(1, 4);
+    grace::device_vector<int> d_csr(csr);
+    grace::device_vector<float> d_data(data), d_results(count), d_weights(weights), d_wsum(count);
+    grace::device_vector<unsigned> d_map(map);
+    grace::exclusive_segmented_scan(d_csr, d_data, d_results);
+    grace::weighted_exclusive_segmented_scan(d_data, d_weights, d_map, d_csr, d_wsum);
+    grace::device_vector<int> d_segments(count);
+    grace::offsets_to_segments(d_csr, d_segments);
+    const std::vector<float> got = d_results.to_host(), wgot = d_wsum.to_host();
+    const std::vector<int> segs = d_segments.to_host();
+    size_t failures = 0;
+    int dense = 0;        // the reference numbers elements by distinct offsets seen (cuda/sort.cuh:27-40)
+    for (int row = 0; row < rows; ++row) {
+        const int b = csr[row], e = row + 1 < rows ? csr[row + 1] : count;
+        if (row >= 1 && (row == 1 || csr[row] != csr[row - 1])) ++dense;
+        float x = 0, wx = 0;
+        for (int i = b; i < e; ++i) {
+            if (got[i] != x || wgot[i] != wx || segs[i] != dense) ++failures;
+            x += data[i];
+            wx += weights[map[i]] * data[i];
+        }
+    }
+    std::printf("  segmented_scan: %d elements in %d segments (max %d%s), %zu mismatches\n", count, rows,
+                random_size, support_empty ? ", empty allowed" : "", failures);
+    return failures == 0 ? 0 : 1;
+}
+
 static int test_errors()
 {
     int bad = 0;
@@ -187,6 +235,8 @@ int main(int argc, char** argv)
         { "tree_traversal", test_tree_traversal(N, N_rays, 32) },
         { "integrate", test_integrate() },
         { "distance_sort", test_distance_sort() },
+        { "segmented_scan", test_segmented_scan(1000000, 3000, true) + test_segmented_scan(200000, 20, false) +
+                            test_segmented_scan(65537, 70000, true) },
         { "argument errors", test_errors() },
     };
     for (auto& r : results) {

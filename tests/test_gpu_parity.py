@@ -387,3 +387,49 @@ def test_rays_not_multiple_of_32(gb, scene):
     out = torch.empty(33, dtype=torch.int32, device="cuda")
     with pytest.raises(ValueError):           # bintree_trace.cuh:231-238
         gb.trace_hitcounts_sph(dev(rays[:33]), d_s, tree, out)
+
+
+# ----------------------------------------------------------------------------- after the path
+@pytest.mark.parametrize("count,max_seg,empty", [(200000, 3000, True), (50000, 20, False), (70000, 100000, True), (31, 5, True)])
+def test_segmented_scans(gb, count, max_seg, empty):
+    """tests/segmented_scan/segmented_scan.cu:66-160: random segments (empty ones allowed),
+    integer-valued data -> exact equality with the sequential host scan; plus float data within
+    rounding, the fused weights, offsets_to_segments (the reference's numbering) and in-place use."""
+    rng = np.random.default_rng(count + max_seg)
+    sizes = []
+    total = 0
+    while total < count:
+        sz = int(rng.integers(0 if empty else 1, min(max_seg, count - total) + 1))
+        sizes.append(sz)
+        total += sz
+    sizes = np.array(sizes, np.int64)
+    off = (np.cumsum(sizes) - sizes).astype(np.int32)
+    data = rng.integers(1, 10, count).astype(np.float32)
+    weights = rng.integers(1, 5, 37).astype(np.float32)
+    wmap = rng.integers(0, 37, count).astype(np.int32)
+    seg_id = np.repeat(np.arange(len(sizes)), sizes)
+
+    def host_scan(x):
+        c = np.cumsum(x.astype(np.float64))
+        start = np.concatenate([[0.0], c])[off.astype(np.int64)]
+        return c - x - start[seg_id]
+    res = torch.empty(count, dtype=torch.float32, device="cuda")
+    gb.exclusive_segmented_scan(dev(off), dev(data), res)
+    assert np.array_equal(host(res).astype(np.float64), host_scan(data))
+    wres = torch.empty(count, dtype=torch.float32, device="cuda")
+    gb.weighted_exclusive_segmented_scan(dev(data), dev(weights), dev(wmap), dev(off), wres)
+    assert np.array_equal(host(wres).astype(np.float64), host_scan(weights[wmap] * data))
+    inplace = dev(data)
+    gb.exclusive_segmented_scan(dev(off), inplace, inplace)
+    assert torch.equal(inplace, res)
+    fdata = rng.random(count, dtype=np.float32)
+    gb.exclusive_segmented_scan(dev(off), dev(fdata), res)
+    want = host_scan(fdata)
+    assert np.max(np.abs(host(res) - want) / np.maximum(want, 1.0)) < 1e-5
+    segs = torch.zeros(count, dtype=torch.int32, device="cuda")
+    gb.offsets_to_segments(dev(off), segs)
+    flags = np.zeros(len(off), np.int64)
+    if len(off) > 1:
+        flags[1] = 1
+        flags[2:] = off[2:] != off[1:-1]
+    assert np.array_equal(host(segs), np.cumsum(flags)[seg_id])
