@@ -409,7 +409,7 @@ def run_b200(args):
             if refrun.available():
                 h_in = gb.synth_gadget_spheres(n, 1234).cpu().numpy()
                 _, info = refrun.run(h_in, "gen:%d:1234:%.9g:%.9g:%.9g:%.9g" % (r, c, c, c, length),
-                                     args.max_per_leaf, 30, iters=2, lists=False, timeout=600)
+                                     args.max_per_leaf, 30, iters=5, lists=False, timeout=600)
                 ref_ms = info["ms_cumulative"]
                 ref_cuda = {"value": r / ref_ms / 1e3, "unit": "Mrays/s", "ms_cumulative": ref_ms,
                             "ms_hitcounts": info["ms_hitcounts"],
