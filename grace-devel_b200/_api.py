@@ -14,6 +14,7 @@ std::invalid_argument in the reference -> ValueError here; CUDA failures -> Runt
 Every call goes through libgrace_b200.so; nothing here computes on the CPU.
 """
 import ctypes
+import os
 import math
 
 import torch
@@ -31,7 +32,7 @@ __all__ = [
     "uniform_random_rays", "uniform_random_rays_single_octant", "one_to_many_rays",
     "plane_parallel_random_rays", "orthographic_projection_rays", "pinhole_camera_rays",
     "healpix_rays", "synth_gadget_spheres", "exclusive_segmented_scan",
-    "weighted_exclusive_segmented_scan", "offsets_to_segments", "context", "lib", "build_tree", "set_trace_mode", "set_trace_budget", "device_error", "sharded_trace", "tiles_of_rank",
+    "weighted_exclusive_segmented_scan", "offsets_to_segments", "read_gadget", "write_gadget", "gadget_info", "context", "lib", "build_tree", "set_trace_mode", "set_trace_budget", "device_error", "sharded_trace", "tiles_of_rank",
 ]
 
 _c = ctypes
@@ -95,6 +96,9 @@ _scan = _sig("grace_b200_exclusive_scan_i32", [_P, _P, _P, _sz, _P, _P])
 _segscan = _sig("grace_b200_exclusive_segmented_scan_f32", [_P, _P, _sz, _P, _sz, _P, _P])
 _wsegscan = _sig("grace_b200_weighted_exclusive_segmented_scan_f32", [_P, _P, _P, _P, _P, _sz, _sz, _P, _P])
 _off2seg = _sig("grace_b200_offsets_to_segments", [_P, _P, _sz, _P, _sz, _P])
+_gadget_info = _sig("grace_b200_gadget_info", [_c.c_char_p, _P, _P, _P])
+_gadget_read = _sig("grace_b200_read_gadget_f4", [_P, _c.c_char_p, _P, _sz, _P, _P])
+_gadget_write = _sig("grace_b200_write_gadget_f4", [_c.c_char_p, _P, _sz, _sz, _c.c_int])
 _table = _sig("grace_b200_kernel_integral_table", [_c.POINTER(_c.c_int)], _c.POINTER(_c.c_double))
 
 
@@ -582,6 +586,35 @@ def healpix_rays(d_rays, nside, first_pixel, n_rays, ox, oy, oz, length):
     _check(_rays_healpix(context(), _dp(d_rays), n_rays, nside, first_pixel, ox, oy, oz, length,
                          _stream()))
     return d_rays
+
+
+def gadget_info(path):
+    """Header of a Gadget-2 type-1 file: (npart[6], mass[6], n_gas)."""
+    np6 = (_c.c_longlong * 6)()
+    m6 = (_c.c_double * 6)()
+    ng = _c.c_longlong(0)
+    _check(_gadget_info(os.fsencode(path), np6, m6, _c.byref(ng)))
+    return list(np6), list(m6), int(ng.value)
+
+
+def read_gadget(path, d_spheres=None):
+    """tests/helper/read_gadget.cuh:161-167: gas positions + smoothing lengths as float4 records
+    on the current device.  Asynchronous on the current stream after the last file read."""
+    n = gadget_info(path)[2]
+    if d_spheres is None:
+        d_spheres = torch.empty((max(n, 1), 4), dtype=torch.float32, device="cuda")
+    _need(d_spheres, torch.float32, "d_spheres", 4)
+    got = _c.c_size_t(0)
+    _check(_gadget_read(context(), os.fsencode(path), _dp(d_spheres), d_spheres.shape[0], _c.byref(got), _stream()))
+    return d_spheres[: got.value]
+
+
+def write_gadget(path, spheres, n_other=0, other_has_mass_block=False):
+    """Driver utility: host float4 records -> a Gadget-2 type-1 file the reference's reader loads."""
+    h = spheres.detach().cpu().contiguous() if isinstance(spheres, torch.Tensor) else torch.from_numpy(spheres).contiguous()
+    if h.dtype != torch.float32 or h.dim() != 2 or h.shape[1] != 4:
+        raise TypeError("spheres must be float32 [N, 4]")
+    _check(_gadget_write(os.fsencode(path), _c.c_void_p(h.data_ptr()), h.shape[0], n_other, int(other_has_mass_block)))
 
 
 def synth_gadget_spheres(n, seed=1234, device=None):

@@ -83,6 +83,10 @@ int grace_b200_destroy(grace_b200_ctx* ctx)
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->d_scalars) cudaFree(ctx->d_scalars);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->stage_host[i]) cudaFreeHost(ctx->stage_host[i]);
+        if (ctx->stage_done[i]) cudaEventDestroy(ctx->stage_done[i]);
+    }
     delete ctx;
     return GRACE_B200_OK;
 }

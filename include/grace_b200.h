@@ -293,6 +293,26 @@ int grace_b200_synth_gadget_f4(grace_b200_ctx* ctx, float* d_spheres4, size_t n,
 int grace_b200_exclusive_scan_i32(grace_b200_ctx* ctx, const int* d_in, int* d_out, size_t n,
                                   long long* d_total, void* stream);
 
+/* ---- before the path: Gadget-2 (type 1) snapshots ------------ */
+/* replaces: read_gadget (tests/helper/read_gadget.cuh:69-167): gas positions + smoothing
+ * lengths -> float4 {x,y,z,h} records on the device.  Block offsets are derived from the
+ * header; the data are read in chunks through pinned staging buffers with the host read of
+ * chunk c+1 overlapping the H2D copy of chunk c, ordered on `stream` (asynchronous after the
+ * last read: queue the build behind it).  *n_gas receives the gas particle count;
+ * GRACE_B200_ERANGE if it exceeds `capacity` (records), GRACE_B200_EINVAL for an unreadable /
+ * truncated file or one without gas particles (read_gadget.cuh:85-90 throws for that). */
+int grace_b200_read_gadget_f4(grace_b200_ctx* ctx, const char* path, float* d_spheres4, size_t capacity,
+                              size_t* n_gas, void* stream);
+/* Header only: npart[6], mass[6] (either may be NULL), gas count. */
+int grace_b200_gadget_info(const char* path, long long* npart6, double* mass6, long long* n_gas);
+/* Writes float4 {x,y,z,h} host records as a Gadget-2 type-1 file the reference's reader loads
+ * (driver utility: SURVEY.md 8d asks for the synthetic snapshot on disk so the unmodified
+ * reference drivers can read the same bytes).  n_other particles of type 1 are appended to
+ * every all-particle block; other_has_mass_block != 0 gives them header mass 0 and hence a
+ * MASS block. */
+int grace_b200_write_gadget_f4(const char* path, const float* h_spheres4, size_t n_gas, size_t n_other,
+                               int other_has_mass_block);
+
 /* ---- after the path: scans along sorted hit lists ------------- */
 /* replaces: exclusive_segmented_scan (cuda/scan.cuh:15-38).  d_results[i] = sum of
  * d_data[segment start .. i); segment s = [offsets[s], offsets[s+1]) and the last one ends at

@@ -127,6 +127,32 @@ if 4 in want:
         list_sum_vs_cumulative_max_rel=rel), exclusive_segmented_scan=scan_info)
     del rays, cum
 
+if 6 in want:     # N1: Gadget-2 snapshot -> device float4 records (the step before the path)
+    import subprocess, tempfile
+    n6 = 1 << args.log2_n
+    h6 = gb.synth_gadget_spheres(n6, 1234).cpu()
+    d = tempfile.mkdtemp(dir="/tmp")
+    path = os.path.join(d, "snap.gdt")
+    gb.write_gadget(path, h6)
+    dst = torch.empty((n6, 4), dtype=torch.float32, device="cuda")
+    ts = []
+    for k in range(4):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        gb.read_gadget(path, dst); torch.cuda.synchronize()
+        ts.append(time.perf_counter() - t0)
+    ok = bool(torch.equal(dst.cpu().view(torch.int32), h6.view(torch.int32)))
+    info = dict(n=n6, file_bytes=os.path.getsize(path), bytes_read=16 * n6, seconds_first=ts[0], seconds=min(ts[1:]),
+                gb_s=16 * n6 / min(ts[1:]) / 1e9, equals_input=ok,
+                note="file in the page cache; wall clock from the call to the last record on the device")
+    ref = os.path.join(ROOT, "oracle", "_ref", "ref_gadget_driver")
+    if os.path.exists(ref):
+        r = subprocess.run([ref, path, os.path.join(d, "ref.bin")], capture_output=True, text=True, timeout=900)
+        if r.returncode == 0:
+            info["reference_reader_seconds"] = json.loads(r.stdout.strip().splitlines()[-1])["seconds_file_to_device"]
+    import shutil; shutil.rmtree(d, ignore_errors=True)
+    out["n1_read_gadget"] = info
+    del dst, h6
+
 if 5 in want:
     del_s = None
     if want & {2, 3, 4}: del s, tree

@@ -14,6 +14,7 @@
 #include "grace/cuda/trace_sph.cuh"
 #include "grace/cuda/util/extrema.cuh"
 #include "grace/generic/intersect.h"
+#include "grace/io/gadget.h"
 #include "grace/generic/morton.h"
 
 #include <algorithm>
@@ -205,6 +206,27 @@ static int test_segmented_scan(int count, int random_size, bool support_empty)
     return failures == 0 ? 0 : 1;
 }
 
+// the reference's drivers start with read_gadget(fname, d_spheres) (tests/profile_tree_gadget/
+// profile_tree_gadget.cu:66-70): write a snapshot, load it, compare.
+static int test_read_gadget()
+{
+    const size_t N = 70000;
+    std::vector<float4> h = random_spheres(N, make_float4(0, 0, 0, 0.001f), make_float4(1, 1, 1, 0.02f));
+    const char* path = "/tmp/grace_b200_shim_test.gdt";
+    if (grace_b200_write_gadget_f4(path, &h[0].x, N, 321, 1) != GRACE_B200_OK) return 1;
+    grace::device_vector<float4> d_spheres;
+    grace::read_gadget(path, d_spheres);
+    const std::vector<float4> back = d_spheres.to_host();
+    size_t bad = back.size() != N;
+    for (size_t i = 0; i < N && !bad; ++i)
+        bad += back[i].x != h[i].x || back[i].y != h[i].y || back[i].z != h[i].z || back[i].w != h[i].w;
+    bool threw = false;
+    try { grace::read_gadget("/tmp/grace_b200_no_such_file.gdt", d_spheres); } catch (const std::runtime_error&) { threw = true; }
+    std::remove(path);
+    std::printf("  read_gadget: %zu gas particles, %zu mismatches\n", back.size(), bad);
+    return bad == 0 && threw ? 0 : 1;
+}
+
 static int test_errors()
 {
     int bad = 0;
@@ -237,6 +259,7 @@ int main(int argc, char** argv)
         { "distance_sort", test_distance_sort() },
         { "segmented_scan", test_segmented_scan(1000000, 3000, true) + test_segmented_scan(200000, 20, false) +
                             test_segmented_scan(65537, 70000, true) },
+        { "read_gadget", test_read_gadget() },
         { "argument errors", test_errors() },
     };
     for (auto& r : results) {
