@@ -183,9 +183,10 @@ def set_trace_mode(mode):
         context(), {"ray": 0, "packet": 1, "packet_ref": 2, "packet_wide": 3}[mode]))
 
 
-def set_trace_budget(steps):
-    """Traversal steps before a packet may be split into ray-subset tasks (0 = never)."""
-    _check(_sig("grace_b200_set_trace_budget", [_P, _c.c_int])(context(), int(steps)))
+def set_trace_budget(steps, eager=False):
+    """Steps before a still-running packet may be split once no unclaimed packet is left
+    (eager=True: split at `steps` regardless; 0: never)."""
+    _check(_sig("grace_b200_set_trace_budget", [_P, _c.c_int])(context(), int(steps) | ((1 << 30) if eager else 0)))
 
 
 def device_error():

@@ -443,7 +443,7 @@ int launch_packet(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, int n_packe
     // Load balancing rounds: 0 = packets, then suspended traversals resumed as tasks over
     // 8, 2 and finally 1 ray(s); the last round runs to completion.  Rounds with nothing to
     // do cost one empty launch.  Disabled (single round) for the profile counters.
-    const bool split = (d_prof == nullptr) && ctx->trace_budget > 0 && n_packets >= 64;
+    const bool split = (d_prof == nullptr) && (ctx->trace_budget & 0x3fffffff) > 0 && n_packets >= 64;
     const int records_cap = split ? (int)std::min<size_t>(std::max<size_t>((size_t)n_packets / 4, 1024), 32768) : 0;
     const int tasks_cap = 4 * records_cap;
     int* records = nullptr;
@@ -473,7 +473,8 @@ int launch_packet(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, int n_packe
         PkTasks T = {};
         if (split) {
             T.records = records; T.n_records = n_counts; T.records_cap = records_cap; T.tasks_cap = tasks_cap;
-            T.budget = ctx->trace_budget;
+            T.budget = ctx->trace_budget & 0x3fffffff;
+            T.eager = (ctx->trace_budget & GRACE_B200_BUDGET_EAGER) ? 1 : 0;
             if (round > 0) { T.tasks_in = lists[(round - 1) & 1]; T.n_tasks_in = n_counts + 1 + ((round - 1) & 1); }
             if (round < n_rounds - 1) {
                 T.tasks_out = lists[round & 1]; T.n_tasks_out = n_counts + 1 + (round & 1);

@@ -426,6 +426,7 @@ struct PkTasks {
     int* n_records;
     int tasks_cap, records_cap;
     int budget;               // steps (inner nodes + leaves) before a unit may be suspended
+    int eager;                // 0: suspend only once every unit of the launch has been claimed
     int child_width;          // lanes per child task
 };
 
@@ -563,7 +564,11 @@ trace_packet_kernel(const PkArgs P, const PkTasks T)
         bool suspended = false;
         for (;;) {
             // ---- suspend an over-budget traversal and hand its rays to several tasks ----
-            if (T.tasks_out && guard0 - guard >= T.budget && (WIDE ? sp > 0 : top >= 0)) {
+            // Splitting costs SIMD width (a task owns fewer rays), so it only pays when warps
+            // would otherwise idle: a unit is suspended once it has run `budget` steps AND the
+            // ticket counter shows that no unclaimed unit is left in this launch.
+            if (T.tasks_out && guard0 - guard >= T.budget && (WIDE ? sp > 0 : top >= 0) &&
+                (T.eager || *(volatile int*)P.unit_counter >= n_units)) {
                 const unsigned bmask0 = T.child_width >= 32 ? 0xffffffffu : ((1u << T.child_width) - 1u);
                 unsigned blocks = 0;          // bit b: some ray of lane block b belongs to this unit
                 for (int b = 0; b * T.child_width < 32; ++b)

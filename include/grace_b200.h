@@ -167,10 +167,13 @@ typedef struct {
 #define GRACE_B200_TRACE_PACKET_REF 2
 #define GRACE_B200_TRACE_PACKET_WIDE 3
 int grace_b200_set_trace_mode(grace_b200_ctx* ctx, int mode);
-/* Load balancing of the PACKET schedule: a packet whose traversal exceeds `steps` inner-node
- * + leaf visits is suspended and resumed as several tasks over disjoint subsets of its rays
- * (results are unaffected: each ray accumulates in the same order).  0 disables splitting;
- * the default is 2048. */
+/* Load balancing of the PACKET schedules: once every packet of a launch has been claimed, a
+ * packet still running after `steps` inner-node + leaf visits is suspended and resumed as
+ * several tasks over disjoint subsets of its rays, so the tail of heavy packets spreads over the
+ * idle SMs (results are unaffected: each ray accumulates in the same order).  0 disables
+ * splitting; the default is 2048.  OR-ing GRACE_B200_BUDGET_EAGER into `steps` suspends every
+ * packet at `steps` whether or not unclaimed work is left (used by the tests to force splits). */
+#define GRACE_B200_BUDGET_EAGER (1 << 30)
 int grace_b200_set_trace_budget(grace_b200_ctx* ctx, int steps);
 /* Device-side error flag of the last trace launch: 0 = none, 1 = traversal stack overflow
  * (the reference asserts on this only under GRACE_DEBUG, bintree_trace.cuh:162-164),

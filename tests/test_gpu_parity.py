@@ -273,7 +273,7 @@ def test_packet_splitting_is_exact(gb, orc, scene, budget, trace_mode):
     if trace_mode not in ("packet", "packet_wide"):
         pytest.skip("splitting exists only in the production packet schedule")
     d_s, tree, hs, htree, rays = scene
-    gb.set_trace_budget(budget)
+    gb.set_trace_budget(budget, eager=True)
     try:
         d_rays = dev(rays)
         cnt = torch.empty(len(rays), dtype=torch.int32, device="cuda")
