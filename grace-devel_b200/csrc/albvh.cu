@@ -288,7 +288,9 @@ leaves_kernel(const T* __restrict__ deltas_shifted, int n, int mpl,
 // Karras/Apetrei way through one arrival counter per node.
 constexpr int ND_THREADS = 256;
 
-template <typename T>
+// FROM_AABB: `spheres` holds two float4 per primitive, {bx,by,bz,-} {tx,ty,tz,-}: boxes a user's
+// AABB functor produced (generic primitives), instead of {x,y,z,h} spheres.
+template <typename T, bool FROM_AABB>
 __global__ void __launch_bounds__(ND_THREADS)
 nodes_kernel(const float4* __restrict__ spheres, const int4* __restrict__ leaves,
              const int* __restrict__ n_leaves_ptr, const T* __restrict__ ld_shifted,
@@ -313,11 +315,17 @@ nodes_kernel(const float4* __restrict__ spheres, const int4* __restrict__ leaves
     // the lines it touches are consumed in full
 #pragma unroll 4
     for (int i = 0; i < lf.y; ++i) {
-        const float4 s = __ldg(spheres + lf.x + i);
-        // AABBSphere, generic/functors/aabb.h:9-26: centre -/+ h, one FADD each
-        bx = fminf(bx, __fsub_rn(s.x, s.w)); tx = fmaxf(tx, __fadd_rn(s.x, s.w));
-        by = fminf(by, __fsub_rn(s.y, s.w)); ty = fmaxf(ty, __fadd_rn(s.y, s.w));
-        bz = fminf(bz, __fsub_rn(s.z, s.w)); tz = fmaxf(tz, __fadd_rn(s.z, s.w));
+        if (FROM_AABB) {
+            const float4 b = __ldg(spheres + 2 * (size_t)(lf.x + i)), t = __ldg(spheres + 2 * (size_t)(lf.x + i) + 1);
+            bx = fminf(bx, b.x); by = fminf(by, b.y); bz = fminf(bz, b.z);
+            tx = fmaxf(tx, t.x); ty = fmaxf(ty, t.y); tz = fmaxf(tz, t.z);
+        } else {
+            const float4 s = __ldg(spheres + lf.x + i);
+            // AABBSphere, generic/functors/aabb.h:9-26: centre -/+ h, one FADD each
+            bx = fminf(bx, __fsub_rn(s.x, s.w)); tx = fmaxf(tx, __fadd_rn(s.x, s.w));
+            by = fminf(by, __fsub_rn(s.y, s.w)); ty = fmaxf(ty, __fadd_rn(s.y, s.w));
+            bz = fminf(bz, __fsub_rn(s.z, s.w)); tz = fmaxf(tz, __fadd_rn(s.z, s.w));
+        }
     }
 
     // ---- (2) nodes inside the warp's window ----
@@ -414,7 +422,7 @@ int grid_cap(const grace_b200_ctx* ctx, size_t work_items, int per_block, int pe
 
 template <typename T>
 int build_typed(grace_b200_ctx* ctx, const float4* d_spheres, size_t n, const T* d_deltas,
-                int mpl, int4* d_nodes, int4* d_leaves, int* d_root, cudaStream_t st)
+                int mpl, int4* d_nodes, int4* d_leaves, int* d_root, cudaStream_t st, bool from_aabb = false)
 {
     const int n_nodes = (int)n - 1;
     const int lv_blocks = (n_nodes + LV_TILE - 1) / LV_TILE;
@@ -452,8 +460,12 @@ int build_typed(grace_b200_ctx* ctx, const float4* d_spheres, size_t n, const T*
     // The leaf count is only known on the device (anything up to n): warps stride over
     // 32-leaf windows.
     const int nd_blocks = grid_cap(ctx, n, ND_THREADS, 8);
-    nodes_kernel<T><<<nd_blocks, ND_THREADS, 0, st>>>(d_spheres, d_leaves, d_nleaves, leaf_deltas,
-                                                       d_nodes, flags, d_root);
+    if (from_aabb)
+        nodes_kernel<T, true><<<nd_blocks, ND_THREADS, 0, st>>>(d_spheres, d_leaves, d_nleaves, leaf_deltas,
+                                                                 d_nodes, flags, d_root);
+    else
+        nodes_kernel<T, false><<<nd_blocks, ND_THREADS, 0, st>>>(d_spheres, d_leaves, d_nleaves, leaf_deltas,
+                                                                  d_nodes, flags, d_root);
     GB_LAUNCH_CHECK();
     return GRACE_B200_OK;
 }
@@ -463,6 +475,8 @@ int launch_simple(const grace_b200_ctx* ctx, size_t n) { return grid_cap(ctx, n 
 } // namespace
 
 extern "C" {
+
+int grace_b200_albvh_last_n_leaves(grace_b200_ctx* ctx, int* h_n_leaves, void* stream);
 
 int grace_b200_deltas_euclid_f4(grace_b200_ctx* ctx, const float* d_spheres4, size_t n,
                                 float* d_deltas, void* stream)
@@ -502,12 +516,11 @@ int grace_b200_deltas_xor64(grace_b200_ctx* ctx, const uint64_t* d_keys, size_t 
     return GRACE_B200_OK;
 }
 
-int grace_b200_albvh_build_f4(grace_b200_ctx* ctx, const float* d_spheres4, size_t n,
-                              const void* d_deltas, int delta_type, int max_per_leaf,
-                              void* d_nodes, void* d_leaves, int* d_root, int* h_n_leaves,
-                              void* stream)
+static int albvh_build_any(grace_b200_ctx* ctx, const float* d_prims, bool from_aabb, size_t n,
+                           const void* d_deltas, int delta_type, int max_per_leaf,
+                           void* d_nodes, void* d_leaves, int* d_root, int* h_n_leaves, void* stream)
 {
-    GB_REQUIRE(ctx && d_spheres4 && d_deltas && d_nodes && d_leaves && d_root, GRACE_B200_EINVAL,
+    GB_REQUIRE(ctx && d_prims && d_deltas && d_nodes && d_leaves && d_root, GRACE_B200_EINVAL,
                "NULL argument");
     GB_REQUIRE(max_per_leaf >= 1, GRACE_B200_EINVAL, "max_per_leaf must be >= 1");
     // albvh.cuh:795-799
@@ -517,19 +530,37 @@ int grace_b200_albvh_build_f4(grace_b200_ctx* ctx, const float* d_spheres4, size
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
     if (delta_type == GRACE_B200_DELTA_F32)
-        rc = build_typed<float>(ctx, (const float4*)d_spheres4, n, (const float*)d_deltas,
-                                max_per_leaf, (int4*)d_nodes, (int4*)d_leaves, d_root, st);
+        rc = build_typed<float>(ctx, (const float4*)d_prims, n, (const float*)d_deltas,
+                                max_per_leaf, (int4*)d_nodes, (int4*)d_leaves, d_root, st, from_aabb);
     else if (delta_type == GRACE_B200_DELTA_U32)
-        rc = build_typed<uint32_t>(ctx, (const float4*)d_spheres4, n, (const uint32_t*)d_deltas,
-                                   max_per_leaf, (int4*)d_nodes, (int4*)d_leaves, d_root, st);
+        rc = build_typed<uint32_t>(ctx, (const float4*)d_prims, n, (const uint32_t*)d_deltas,
+                                   max_per_leaf, (int4*)d_nodes, (int4*)d_leaves, d_root, st, from_aabb);
     else if (delta_type == GRACE_B200_DELTA_U64)
-        rc = build_typed<uint64_t>(ctx, (const float4*)d_spheres4, n, (const uint64_t*)d_deltas,
-                                   max_per_leaf, (int4*)d_nodes, (int4*)d_leaves, d_root, st);
+        rc = build_typed<uint64_t>(ctx, (const float4*)d_prims, n, (const uint64_t*)d_deltas,
+                                   max_per_leaf, (int4*)d_nodes, (int4*)d_leaves, d_root, st, from_aabb);
     else
         return gb_set_error(GRACE_B200_EINVAL, "unknown delta_type %d", delta_type);
     if (rc) return rc;
     if (h_n_leaves) return grace_b200_albvh_last_n_leaves(ctx, h_n_leaves, stream);
     return GRACE_B200_OK;
+}
+
+int grace_b200_albvh_build_f4(grace_b200_ctx* ctx, const float* d_spheres4, size_t n,
+                              const void* d_deltas, int delta_type, int max_per_leaf,
+                              void* d_nodes, void* d_leaves, int* d_root, int* h_n_leaves,
+                              void* stream)
+{
+    return albvh_build_any(ctx, d_spheres4, false, n, d_deltas, delta_type, max_per_leaf, d_nodes, d_leaves,
+                           d_root, h_n_leaves, stream);
+}
+
+int grace_b200_albvh_build_aabb(grace_b200_ctx* ctx, const float* d_aabbs8, size_t n,
+                                const void* d_deltas, int delta_type, int max_per_leaf,
+                                void* d_nodes, void* d_leaves, int* d_root, int* h_n_leaves,
+                                void* stream)
+{
+    return albvh_build_any(ctx, d_aabbs8, true, n, d_deltas, delta_type, max_per_leaf, d_nodes, d_leaves,
+                           d_root, h_n_leaves, stream);
 }
 
 int grace_b200_albvh_last_n_leaves(grace_b200_ctx* ctx, int* h_n_leaves, void* stream)

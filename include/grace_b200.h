@@ -140,6 +140,14 @@ int grace_b200_albvh_build_f4(grace_b200_ctx* ctx, const float* d_spheres4, size
                               void* d_nodes, void* d_leaves, int* d_root,
                               int* h_n_leaves, void* stream);
 int grace_b200_albvh_last_n_leaves(grace_b200_ctx* ctx, int* h_n_leaves, void* stream);
+/* replaces: build_ALBVH(tree, primitives, deltas, AABBFunc) for arbitrary primitive types
+ * (cuda/kernels/albvh.cuh:986-1072): the caller evaluates its AABB functor
+ * (include/grace/cuda/kernels/albvh.cuh here does) into d_aabbs8 = two float4 per primitive,
+ * {bx,by,bz,-} {tx,ty,tz,-}; everything else as grace_b200_albvh_build_f4. */
+int grace_b200_albvh_build_aabb(grace_b200_ctx* ctx, const float* d_aabbs8, size_t n,
+                                const void* d_deltas, int delta_type, int max_per_leaf,
+                                void* d_nodes, void* d_leaves, int* d_root, int* h_n_leaves,
+                                void* stream);
 
 /* ---- trace ------------------------------------------------------------------ */
 /* A tree as the trace entry points take it (grace::Tree, cuda/nodes.h:14-58). */

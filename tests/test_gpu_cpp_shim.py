@@ -16,4 +16,4 @@ def test_cpp_shim_programs(gb):
     out = subprocess.run([BIN, "200000", "200"], capture_output=True, text=True, timeout=600)
     print(out.stdout[-3000:], out.stderr[-2000:])
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
-    assert out.stdout.count("PASSED") == 5 and "FAILED" not in out.stdout
+    assert out.stdout.count("PASSED") == 7 and "FAILED" not in out.stdout
