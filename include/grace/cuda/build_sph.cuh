@@ -17,7 +17,7 @@ inline void keys(const float4* s, size_t n, const float* d_bounds6, uinteger64* 
 } // namespace detail
 
 // Keys from the bounds of the sphere centres.
-template <typename SphereVec, typename KeyVec>
+template <typename SphereVec, typename KeyVec, detail::if_elem<SphereVec, float4> = 0>
 GRACE_HOST void morton_keys_sph(const SphereVec& d_spheres, KeyVec& d_keys)
 {
     float* d_b = nullptr;
@@ -30,7 +30,7 @@ GRACE_HOST void morton_keys_sph(const SphereVec& d_spheres, KeyVec& d_keys)
 }
 
 // Keys from explicit bounds.
-template <typename Real3, typename SphereVec, typename KeyVec>
+template <typename Real3, typename SphereVec, typename KeyVec, detail::if_elem<SphereVec, float4> = 0>
 GRACE_HOST void morton_keys_sph(const SphereVec& d_spheres, const Real3 bot, const Real3 top, KeyVec& d_keys)
 {
     const float h[6] = { (float)bot.x, (float)bot.y, (float)bot.z, (float)top.x, (float)top.y, (float)top.z };
@@ -42,26 +42,26 @@ GRACE_HOST void morton_keys_sph(const SphereVec& d_spheres, const Real3 bot, con
     cudaFree(d_b);
 }
 
-template <typename SphereVec>
+template <typename SphereVec, detail::if_elem<SphereVec, float4> = 0>
 GRACE_HOST void morton_keys30_sort_sph(SphereVec& d_spheres)
 {
     GRACE_B200_CHECK(grace_b200_morton_sort_f4(detail::context(), detail::f4(detail::raw(d_spheres.data())),
                                                d_spheres.size(), 30, nullptr, nullptr, nullptr, nullptr));
 }
-template <typename Real3, typename SphereVec>
+template <typename Real3, typename SphereVec, detail::if_elem<SphereVec, float4> = 0>
 GRACE_HOST void morton_keys30_sort_sph(SphereVec& d_spheres, const Real3 bot, const Real3 top)
 {
     const float b[3] = { (float)bot.x, (float)bot.y, (float)bot.z }, t[3] = { (float)top.x, (float)top.y, (float)top.z };
     GRACE_B200_CHECK(grace_b200_morton_sort_f4(detail::context(), detail::f4(detail::raw(d_spheres.data())),
                                                d_spheres.size(), 30, b, t, nullptr, nullptr));
 }
-template <typename SphereVec>
+template <typename SphereVec, detail::if_elem<SphereVec, float4> = 0>
 GRACE_HOST void morton_keys63_sort_sph(SphereVec& d_spheres)
 {
     GRACE_B200_CHECK(grace_b200_morton_sort_f4(detail::context(), detail::f4(detail::raw(d_spheres.data())),
                                                d_spheres.size(), 63, nullptr, nullptr, nullptr, nullptr));
 }
-template <typename Real3, typename SphereVec>
+template <typename Real3, typename SphereVec, detail::if_elem<SphereVec, float4> = 0>
 GRACE_HOST void morton_keys63_sort_sph(SphereVec& d_spheres, const Real3 bot, const Real3 top)
 {
     const float b[3] = { (float)bot.x, (float)bot.y, (float)bot.z }, t[3] = { (float)top.x, (float)top.y, (float)top.z };
@@ -69,13 +69,13 @@ GRACE_HOST void morton_keys63_sort_sph(SphereVec& d_spheres, const Real3 bot, co
                                                d_spheres.size(), 63, b, t, nullptr, nullptr));
 }
 
-template <typename SphereVec, typename DeltaVec>
+template <typename SphereVec, typename DeltaVec, detail::if_elem<SphereVec, float4> = 0>
 GRACE_HOST void euclidean_deltas_sph(const SphereVec& d_spheres, DeltaVec& d_deltas)
 {
     GRACE_B200_CHECK(grace_b200_deltas_euclid_f4(detail::context(), detail::f4(detail::raw(d_spheres.data())),
                                                  d_spheres.size(), detail::raw(d_deltas.data()), nullptr));
 }
-template <typename SphereVec, typename DeltaVec>
+template <typename SphereVec, typename DeltaVec, detail::if_elem<SphereVec, float4> = 0>
 GRACE_HOST void surface_area_deltas_sph(const SphereVec& d_spheres, DeltaVec& d_deltas)
 {
     GRACE_B200_CHECK(grace_b200_deltas_sarea_f4(detail::context(), detail::f4(detail::raw(d_spheres.data())),
@@ -95,7 +95,7 @@ GRACE_HOST void XOR_deltas_sph(const KeyVec& d_keys, DeltaVec& d_deltas)
 }
 
 // Throws std::invalid_argument if the number of spheres is <= tree.max_per_leaf.
-template <typename SphereVec, typename DeltaVec>
+template <typename SphereVec, typename DeltaVec, detail::if_elem<SphereVec, float4> = 0>
 GRACE_HOST void ALBVH_sph(const SphereVec& d_spheres, const DeltaVec& d_deltas, Tree& d_tree)
 {
     int L = 0;
@@ -109,3 +109,7 @@ GRACE_HOST void ALBVH_sph(const SphereVec& d_spheres, const DeltaVec& d_deltas, 
 }
 
 } // namespace grace
+
+#ifdef __CUDACC__
+#include "grace/cuda/sph_double.cuh"   // double4 spheres through the header templates
+#endif

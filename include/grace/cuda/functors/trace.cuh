@@ -9,6 +9,7 @@
 #include "grace/cuda/util/bound_iter.cuh"
 #include "grace/generic/interpolate.h"
 #include "grace/generic/intersect.h"
+#include "grace/generic/meta.h"
 #include "grace/ray.h"
 #include "grace/types.h"
 
@@ -69,7 +70,8 @@ public:
     template <typename Real4, typename RayData>
     __device__ bool operator()(const Ray& ray, const Real4& sphere, const RayData&, const int, const gpu::BoundIter<char>)
     {
-        float b2, dist;
+        typedef typename Real4ToRealMapper<Real4>::type Real;
+        Real b2, dist;
         return sphere_hit(ray, sphere, b2, dist);
     }
 };
@@ -103,10 +105,11 @@ public:
     __device__ void operator()(const int, const Ray&, RayData& ray_data, const int, const Real4& sphere, const int,
                                const gpu::BoundIter<char> smem_iter)
     {
+        typedef typename Real4ToRealMapper<Real4>::type Real;
         gpu::BoundIter<double> Wk_lookup = smem_iter;
-        float ir = 1.f / sphere.w;
-        float b = (N_table - 1) * (sqrtf(ray_data.b2) * ir);
-        float integral = lerp(b, Wk_lookup, N_table);
+        Real ir = 1.f / sphere.w;
+        Real b = (N_table - 1) * (sqrt(ray_data.b2) * ir);
+        Real integral = lerp(b, Wk_lookup, N_table);
         integral *= (ir * ir);
         ray_data.data += integral;
     }
@@ -125,10 +128,11 @@ public:
     __device__ void operator()(const int, const Ray&, RayData& ray_data, const int sphere_idx, const Real4& sphere,
                                const int, const gpu::BoundIter<char> smem_iter)
     {
+        typedef typename Real4ToRealMapper<Real4>::type Real;
         gpu::BoundIter<double> Wk_lookup = smem_iter;
-        float ir = 1.f / sphere.w;
-        float b = (N_table - 1) * (sqrtf(ray_data.b2) * ir);
-        float integral = lerp(b, Wk_lookup, N_table);
+        Real ir = 1.f / sphere.w;
+        Real b = (N_table - 1) * (sqrt(ray_data.b2) * ir);
+        Real integral = lerp(b, Wk_lookup, N_table);
         integral *= (ir * ir);
         indices[ray_data.data] = sphere_idx;
         integrals[ray_data.data] = integral;

@@ -30,7 +30,7 @@ inline const grace_b200_ray* rays_ptr(const Ray* r) { return reinterpret_cast<co
 }
 
 // All throw std::invalid_argument unless d_rays.size() % 32 == 0.
-template <typename RayVec, typename SphereVec, typename IntVec>
+template <typename RayVec, typename SphereVec, typename IntVec, detail::if_elem<SphereVec, float4> = 0>
 GRACE_HOST void trace_hitcounts_sph(const RayVec& d_rays, const SphereVec& d_spheres, const Tree& d_tree,
                                     IntVec& d_hit_counts)
 {
@@ -41,7 +41,7 @@ GRACE_HOST void trace_hitcounts_sph(const RayVec& d_rays, const SphereVec& d_sph
         detail::raw(d_hit_counts.data()), nullptr));
 }
 
-template <typename RayVec, typename SphereVec, typename RealVec>
+template <typename RayVec, typename SphereVec, typename RealVec, detail::if_elem<SphereVec, float4> = 0>
 GRACE_HOST void trace_cumulative_sph(const RayVec& d_rays, const SphereVec& d_spheres, const Tree& d_tree,
                                      RealVec& d_cumulated)
 {
@@ -82,7 +82,7 @@ inline void trace_lists(const RayVec& d_rays, const SphereVec& d_spheres, const 
 } // namespace detail
 
 // d_ray_offsets must hold one int per ray; the three hit vectors are resized by the call.
-template <typename RayVec, typename SphereVec, typename IntVec, typename IdxVec, typename RealVec>
+template <typename RayVec, typename SphereVec, typename IntVec, typename IdxVec, typename RealVec, detail::if_elem<SphereVec, float4> = 0>
 GRACE_HOST void trace_sph(const RayVec& d_rays, const SphereVec& d_spheres, const Tree& d_tree, IntVec& d_ray_offsets,
                           IdxVec& d_hit_indices, RealVec& d_hit_integrals, RealVec& d_hit_distances)
 {
@@ -91,7 +91,7 @@ GRACE_HOST void trace_sph(const RayVec& d_rays, const SphereVec& d_spheres, cons
 }
 
 // Each ray's segment ends with one slot holding the sentinels.
-template <typename RayVec, typename SphereVec, typename IntVec, typename IdxVec, typename RealVec, typename Real>
+template <typename RayVec, typename SphereVec, typename IntVec, typename IdxVec, typename RealVec, typename Real, detail::if_elem<SphereVec, float4> = 0>
 GRACE_HOST void trace_with_sentinels_sph(const RayVec& d_rays, const SphereVec& d_spheres, const Tree& d_tree,
                                          IntVec& d_ray_offsets, IdxVec& d_hit_indices, const int index_sentinel,
                                          RealVec& d_hit_integrals, const Real integral_sentinel,
@@ -104,3 +104,7 @@ GRACE_HOST void trace_with_sentinels_sph(const RayVec& d_rays, const SphereVec& 
 }
 
 } // namespace grace
+
+#ifdef __CUDACC__
+#include "grace/cuda/sph_double.cuh"   // double4 spheres through the header templates
+#endif

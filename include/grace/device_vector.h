@@ -4,6 +4,8 @@
 // thrust::device_vector works unchanged in user code that includes Thrust itself.
 #pragma once
 #include <cstddef>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "grace/error.h"
@@ -101,6 +103,15 @@ namespace detail {
 // raw pointer of whatever a container's data() returns: T* or thrust::device_ptr<T>
 template <typename T> inline T* raw(T* p) { return p; }
 template <typename P> inline auto raw(P p) -> decltype(p.get()) { return p.get(); }
+
+// element type of a container (through data()), and SFINAE on it: the float4 entry points go
+// through the C ABI, the double4 ones through the header templates
+template <typename Vec>
+struct elem_of {
+    typedef typename std::remove_cv<typename std::remove_pointer<decltype(raw(std::declval<Vec&>().data()))>::type>::type type;
+};
+template <typename Vec, typename T>
+using if_elem = typename std::enable_if<std::is_same<typename elem_of<Vec>::type, T>::value, int>::type;
 
 // one context per device for the whole process (the reference has no context object)
 inline grace_b200_ctx* context()

@@ -21,6 +21,9 @@ python "$HERE/patch_ref.py" "$REF" "$SCRATCH" > /dev/null
 /usr/local/cuda/bin/nvcc -arch=sm_100 -O3 -std=c++17 -w -Xcompiler -fopenmp \
     -I "$SCRATCH/include" -I "$SCRATCH/tests" -I "$SCRATCH/include/grace/external/sgpu" -I "$HERE/../tests/cpp" \
     "$HERE/ref_generic_driver.cu" -o "$OUT/ref_generic_driver" -lcurand
+/usr/local/cuda/bin/nvcc -arch=sm_100 -O3 -std=c++17 -w -Xcompiler -fopenmp \
+    -I "$SCRATCH/include" -I "$SCRATCH/tests" -I "$SCRATCH/include/grace/external/sgpu" -I "$HERE/../tests/cpp" \
+    "$HERE/ref_sph_double_driver.cu" -o "$OUT/ref_sph_double_driver" -lcurand
 # 2. the reference's host-callable code (unpatched headers)
 /usr/bin/g++ -O3 -fPIC -shared -fopenmp -ffp-contract=off -fvisibility=hidden \
     -I "$REF/include" -I /usr/local/cuda/include "$HERE/ref_cpu.cpp" -o "$OUT/libgrace_ref_cpu.so"
