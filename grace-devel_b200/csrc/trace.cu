@@ -468,6 +468,21 @@ int launch_packet(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, int n_packe
     P.hit_idx = hit_idx; P.hit_integral = hit_integral; P.hit_dist = hit_dist;
     P.unit_counter = counter; P.err_flag = ctx->d_scalars + GB_SC_ERRFLAG; P.prof = d_prof;
     const int widths[3] = { 8, 2, 1 };
+    if (split && ctx->trace_dynamic) {
+        // One launch: suspended traversals go to a queue that the idle warps of the same launch drain.
+        PkTasks T = {};
+        T.records = records; T.n_records = n_counts; T.records_cap = records_cap;
+        T.budget = ctx->trace_budget & 0x3fffffff;
+        T.eager = (ctx->trace_budget & GRACE_B200_BUDGET_EAGER) ? 1 : 0;
+        T.dynamic = 1;
+        T.queue = lists[0]; T.queue_cap = 2 * tasks_cap;        // lists[0] and lists[1] are contiguous
+        T.q_head = n_counts + 1; T.q_tail = n_counts + 2; T.finished = n_counts + 3;
+        GB_CUDA(cudaMemsetAsync(T.queue, 0xff, (size_t)T.queue_cap * 8, st));    // slot.x = -1: not published
+        GB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
+        kernel<<<full_grid, PK_THREADS, psmem, st>>>(P, T);
+        GB_LAUNCH_CHECK();
+        return GRACE_B200_OK;
+    }
     const int n_rounds = split ? 4 : 1;
     for (int round = 0; round < n_rounds; ++round) {
         PkTasks T = {};
@@ -573,6 +588,13 @@ int grace_b200_set_trace_budget(grace_b200_ctx* ctx, int steps)
 {
     GB_REQUIRE(ctx && steps >= 0, GRACE_B200_EINVAL, "bad argument");
     ctx->trace_budget = steps;
+    return GRACE_B200_OK;
+}
+
+int grace_b200_set_trace_dynamic(grace_b200_ctx* ctx, int on)
+{
+    GB_REQUIRE(ctx, GRACE_B200_EINVAL, "ctx is NULL");
+    ctx->trace_dynamic = on ? 1 : 0;
     return GRACE_B200_OK;
 }
 

@@ -428,7 +428,17 @@ struct PkTasks {
     int budget;               // steps (inner nodes + leaves) before a unit may be suspended
     int eager;                // 0: suspend only once every unit of the launch has been claimed
     int child_width;          // lanes per child task
+    // Dynamic mode (single launch): suspended traversals go to a queue that idle warps of the SAME
+    // launch drain.  queue[i] = {record, ray subset} stored as one 64-bit word; record -1 = not
+    // published yet.
+    int dynamic;
+    int2* queue; int queue_cap;
+    int* q_head;              // next slot to claim
+    int* q_tail;              // slots reserved so far
+    int* finished;            // packets + tasks finished so far; the launch is over when it equals
+                              // n_packets + q_tail (every reserved slot is published and consumed)
 };
+constexpr int PK_SPIN_LIMIT = 1 << 20;     // polls (up to ~4 us apart) before an idle warp gives up (error 3)
 
 // Claim `n` consecutive slots of a bounded pool; -1 if they do not fit.
 __device__ __forceinline__ int pk_reserve(int* counter, int n, int cap)
@@ -487,14 +497,57 @@ trace_packet_kernel(const PkArgs P, const PkTasks T)
     const int n_units = T.tasks_in ? min(__ldg(T.n_tasks_in), T.tasks_cap) : P.n_packets;
 
     for (;;) {
-        int unit = 0;
-        if (lane == 0) unit = atomicAdd(P.unit_counter, 1);
+        int unit = -1;
+        int2 task = make_int2(-1, 0);
+        if (lane == 0) {
+            // volatile pre-check keeps the ticket from running away while idle warps poll
+            if (*(volatile int*)P.unit_counter < n_units) unit = atomicAdd(P.unit_counter, 1);
+            if (unit >= n_units) unit = -1;
+            if (unit < 0 && T.dynamic) {
+                // every packet has been claimed: drain the queue of suspended traversals
+                int spins = 0;
+                unsigned backoff = 64;
+                for (;;) {
+                    // `finished` is read BEFORE `q_tail`: both only grow, finished <= n_packets + q_tail
+                    // always holds, so equality of the two samples proves that everything is done
+                    const int f = *(volatile int*)T.finished;
+                    const int t = *(volatile int*)T.q_tail;
+                    const int h = *(volatile int*)T.q_head;
+                    if (h < t) {
+                        if (atomicCAS(T.q_head, h, h + 1) != h) continue;
+                        // reserved before published: wait for the publisher's store
+                        int2 e;
+                        int wait = 0;
+                        do {
+                            const unsigned long long v = *(volatile unsigned long long*)(T.queue + h);
+                            e = make_int2((int)(unsigned)v, (int)(unsigned)(v >> 32));
+                        } while (e.x == -1 && ++wait < PK_SPIN_LIMIT);
+                        if (e.x < 0) { atomicMax(P.err_flag, 3); atomicAdd(T.finished, 1); continue; }
+                        task = e;
+                        unit = n_units + h;
+                        break;
+                    }
+                    if (f >= n_units + t) break;
+                    if (++spins > PK_SPIN_LIMIT) { atomicMax(P.err_flag, 3); break; }
+                    __nanosleep(backoff);
+                    if (backoff < 4096) backoff *= 2;
+                }
+            }
+        }
         unit = __shfl_sync(0xffffffffu, unit, 0);
-        if (unit >= n_units) break;
+        if (unit < 0) break;
         int packet = unit;
         unsigned subset = 0xffffffffu;
         const int* rec = nullptr;
-        if (T.tasks_in) {
+        int level = 0;                    // dynamic mode: how many times this traversal has been split
+        if (T.dynamic && unit >= n_units) {
+            task.x = __shfl_sync(0xffffffffu, task.x, 0);
+            task.y = __shfl_sync(0xffffffffu, task.y, 0);
+            rec = T.records + (size_t)task.x * PK_REC_WORDS;
+            packet = __ldcg(rec + 0);
+            level = __ldcg(rec + 5);
+            subset = (unsigned)task.y;
+        } else if (T.tasks_in) {
             const int2 t = T.tasks_in[unit];
             if (t.x < 0) continue;            // slot claimed but never filled (pool was full)
             rec = T.records + (size_t)t.x * PK_REC_WORDS;
@@ -545,13 +598,15 @@ trace_packet_kernel(const PkArgs P, const PkTasks T)
             sp = 1;
         }
         if (rec) {      // resume a suspended traversal for the rays in `subset`
-            sp = rec[2]; top = rec[3]; top_mask = (unsigned)rec[4] & subset;
-            for (int i = lane; i < sp; i += 32) W.stack[i] = ((const int2*)(rec + 8))[i];
+            // L1-bypassing loads: in dynamic mode the record was written by another SM during this
+            // launch, and a line cached for a neighbouring record may cover its first words
+            sp = __ldcg(rec + 2); top = __ldcg(rec + 3); top_mask = (unsigned)__ldcg(rec + 4) & subset;
+            for (int i = lane; i < sp; i += 32) W.stack[i] = __ldcg((const int2*)(rec + 8) + i);
             __syncwarp();
             if (!WIDE && top_mask == 0u) PK_POP();
-            A.cum = __int_as_float(rec[8 + 2 * PK_STACK + lane]);
-            A.count = rec[8 + 2 * PK_STACK + 32 + lane];
-            A.cursor = rec[8 + 2 * PK_STACK + 64 + lane];
+            A.cum = __int_as_float(__ldcg(rec + 8 + 2 * PK_STACK + lane));
+            A.count = __ldcg(rec + 8 + 2 * PK_STACK + 32 + lane);
+            A.cursor = __ldcg(rec + 8 + 2 * PK_STACK + 64 + lane);
         } else if (MODE == MODE_FILL) {
             A.cursor = P.offsets[ray_index];
         }
@@ -567,22 +622,34 @@ trace_packet_kernel(const PkArgs P, const PkTasks T)
             // Splitting costs SIMD width (a task owns fewer rays), so it only pays when warps
             // would otherwise idle: a unit is suspended once it has run `budget` steps AND the
             // ticket counter shows that no unclaimed unit is left in this launch.
-            if (T.tasks_out && guard0 - guard >= T.budget && (WIDE ? sp > 0 : top >= 0) &&
+            const bool may_split = T.dynamic ? level < 3 : T.tasks_out != nullptr;
+            if (may_split && guard0 - guard >= T.budget && (WIDE ? sp > 0 : top >= 0) &&
                 (T.eager || *(volatile int*)P.unit_counter >= n_units)) {
-                const unsigned bmask0 = T.child_width >= 32 ? 0xffffffffu : ((1u << T.child_width) - 1u);
+                // rays per child task: 8, 2, 1 by round (one launch per round) or by split level (dynamic)
+                const int child_width = T.dynamic ? (level == 0 ? 8 : level == 1 ? 2 : 1) : T.child_width;
+                const unsigned bmask0 = child_width >= 32 ? 0xffffffffu : ((1u << child_width) - 1u);
                 unsigned blocks = 0;          // bit b: some ray of lane block b belongs to this unit
-                for (int b = 0; b * T.child_width < 32; ++b)
-                    if (subset & (bmask0 << (b * T.child_width))) blocks |= 1u << b;
+                for (int b = 0; b * child_width < 32; ++b)
+                    if (subset & (bmask0 << (b * child_width))) blocks |= 1u << b;
                 const int nchild = __popc(blocks);
                 int rslot = -1, tslot = -1;
                 if (nchild > 1 && lane == 0) {
                     // Reserve with compare-and-swap: a counter must never be visible above its
                     // final value (an add-then-undo would let another warp claim slots past it).
-                    tslot = pk_reserve(T.n_tasks_out, nchild, T.tasks_cap);
-                    if (tslot >= 0) {
+                    if (T.dynamic) {
                         rslot = pk_reserve(T.n_records, 1, T.records_cap);
-                        if (rslot < 0) {       // no record: publish nothing in the claimed task slots
-                            for (int c = 0; c < nchild; ++c) T.tasks_out[tslot + c] = make_int2(-1, 0);
+                        if (rslot >= 0) {
+                            tslot = pk_reserve(T.q_tail, nchild, T.queue_cap);
+                            if (tslot < 0) rslot = -1;              // queue full: keep running (the record slot is lost)
+
+                        }
+                    } else {
+                        tslot = pk_reserve(T.n_tasks_out, nchild, T.tasks_cap);
+                        if (tslot >= 0) {
+                            rslot = pk_reserve(T.n_records, 1, T.records_cap);
+                            if (rslot < 0) {       // no record: publish nothing in the claimed task slots
+                                for (int c = 0; c < nchild; ++c) T.tasks_out[tslot + c] = make_int2(-1, 0);
+                            }
                         }
                     }
                 }
@@ -591,17 +658,27 @@ trace_packet_kernel(const PkArgs P, const PkTasks T)
                 if (rslot >= 0) {
                     if (NEED_Q) pk_flush<MODE, M4>(W, A, lane, lt, s_table);
                     int* r = T.records + (size_t)rslot * PK_REC_WORDS;
-                    if (lane == 0) { r[0] = packet; r[1] = (int)subset; r[2] = sp; r[3] = top; r[4] = (int)top_mask; }
+                    if (lane == 0) { r[0] = packet; r[1] = (int)subset; r[2] = sp; r[3] = top; r[4] = (int)top_mask; r[5] = level + 1; }
                     for (int i = lane; i < sp; i += 32) ((int2*)(r + 8))[i] = W.stack[i];
                     r[8 + 2 * PK_STACK + lane] = __float_as_int(A.cum);
                     r[8 + 2 * PK_STACK + 32 + lane] = A.count;
                     r[8 + 2 * PK_STACK + 64 + lane] = A.cursor;
+                    if (T.dynamic) {          // the record must be visible before the queue slots are
+                        __threadfence();
+                        __syncwarp();
+                    }
                     if (lane < nchild) {      // lane c publishes the c-th non-empty block
                         unsigned bb = blocks;
                         for (int c = 0; c < lane; ++c) bb &= bb - 1;
                         const int b = __ffs(bb) - 1;
-                        T.tasks_out[tslot + lane] = make_int2(rslot, (int)(subset & (bmask0 << (b * T.child_width))));
+                        const unsigned child = subset & (bmask0 << (b * child_width));
+                        if (T.dynamic)        // one 64-bit store: a consumer sees all of the slot or none of it
+                            *(volatile unsigned long long*)(T.queue + tslot + lane) =
+                                (unsigned long long)(unsigned)rslot | ((unsigned long long)child << 32);
+                        else
+                            T.tasks_out[tslot + lane] = make_int2(rslot, (int)child);
                     }
+                    if (T.dynamic && lane == 0) atomicAdd(T.finished, 1);       // this unit is done as a unit
                     suspended = true;
                     break;
                 }
@@ -797,6 +874,7 @@ trace_packet_kernel(const PkArgs P, const PkTasks T)
         if (NEED_Q) pk_flush<MODE, M4>(W, A, lane, lt, s_table);
         if (MODE == MODE_COUNT && lane_on) P.out_counts[ray_index] = A.count;
         if (MODE == MODE_CUMULATIVE && lane_on) P.out_cum[ray_index] = A.cum;
+        if (T.dynamic && lane == 0) atomicAdd(T.finished, 1);
         if (PROF && lane == 0) {
             atomicAdd(P.prof + 0, pf_nodes); atomicAdd(P.prof + 1, pf_leaves);
             atomicAdd(P.prof + 2, pf_staged); atomicAdd(P.prof + 3, pf_kept);

@@ -183,6 +183,9 @@ int grace_b200_set_trace_mode(grace_b200_ctx* ctx, int mode);
  * packet at `steps` whether or not unclaimed work is left (used by the tests to force splits). */
 #define GRACE_B200_BUDGET_EAGER (1 << 30)
 int grace_b200_set_trace_budget(grace_b200_ctx* ctx, int steps);
+/* Where suspended traversals are resumed: 0 = in follow-up launches, one per split level (tasks
+ * of 8, 2, 1 rays); 1 = inside the same launch, from a queue the idle warps drain. */
+int grace_b200_set_trace_dynamic(grace_b200_ctx* ctx, int on);
 /* Device-side error flag of the last trace launch: 0 = none, 1 = traversal stack overflow
  * (the reference asserts on this only under GRACE_DEBUG, bintree_trace.cuh:162-164),
  * 2 = traversal did not terminate within 2*n_nodes steps (malformed tree).

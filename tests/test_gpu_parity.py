@@ -266,14 +266,16 @@ def test_hit_lists_and_sort(gb, orc, scene):
     assert np.array_equal(host(integ).view(np.uint32), sg.view(np.uint32))
 
 
+@pytest.mark.parametrize("dynamic", [False, True])
 @pytest.mark.parametrize("budget", [8, 100, 1000])
-def test_packet_splitting_is_exact(gb, orc, scene, budget, trace_mode):
+def test_packet_splitting_is_exact(gb, orc, scene, budget, dynamic, trace_mode):
     """Over-budget packets are suspended and resumed as ray-subset tasks; with a tiny
     budget nearly every packet goes through all four rounds.  Results must not change."""
     if trace_mode not in ("packet", "packet_wide"):
         pytest.skip("splitting exists only in the production packet schedule")
     d_s, tree, hs, htree, rays = scene
     gb.set_trace_budget(budget, eager=True)
+    gb.set_trace_dynamic(dynamic)       # resumed in follow-up launches, or from a queue inside the launch
     try:
         d_rays = dev(rays)
         cnt = torch.empty(len(rays), dtype=torch.int32, device="cuda")
@@ -293,6 +295,7 @@ def test_packet_splitting_is_exact(gb, orc, scene, budget, trace_mode):
         assert np.array_equal(host(dist).view(np.uint32), rdist.view(np.uint32))
     finally:
         gb.set_trace_budget(2048)
+        gb.set_trace_dynamic(False)
 
 
 def test_axis_aligned_and_degenerate_directions(gb, orc, scene):
