@@ -458,7 +458,7 @@ int launch_packet(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, int n_packe
         lists[1] = (int2*)(w + 4096 + rec_bytes + list_bytes);
     }
     int* n_counts = ctx->d_scalars + GB_SC_TASKS;      // [0] records, [1] list 0, [2] list 1
-    if (split) GB_CUDA(cudaMemsetAsync(n_counts, 0, 4 * sizeof(int), st));
+    if (split) GB_CUDA(cudaMemsetAsync(n_counts, 0, 8 * sizeof(int), st));     // + [4,5] step sum (64-bit), [6] units done
     GB_CUDA(cudaMemsetAsync(ctx->d_scalars + GB_SC_ERRFLAG, 0, sizeof(int), st));
     PkArgs P;
     P.rays = d_rays; P.n_packets = n_packets; P.spheres = (const float4*)d_spheres4;
@@ -475,6 +475,7 @@ int launch_packet(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, int n_packe
         T.budget = ctx->trace_budget & 0x3fffffff;
         T.eager = (ctx->trace_budget & GRACE_B200_BUDGET_EAGER) ? 1 : 0;
         T.dynamic = 1;
+        T.sum_steps = (unsigned long long*)(n_counts + 4); T.n_done = n_counts + 6;
         T.queue = lists[0]; T.queue_cap = 2 * tasks_cap;        // lists[0] and lists[1] are contiguous
         T.q_head = n_counts + 1; T.q_tail = n_counts + 2; T.finished = n_counts + 3;
         GB_CUDA(cudaMemsetAsync(T.queue, 0xff, (size_t)T.queue_cap * 8, st));    // slot.x = -1: not published
@@ -490,6 +491,10 @@ int launch_packet(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, int n_packe
             T.records = records; T.n_records = n_counts; T.records_cap = records_cap; T.tasks_cap = tasks_cap;
             T.budget = ctx->trace_budget & 0x3fffffff;
             T.eager = (ctx->trace_budget & GRACE_B200_BUDGET_EAGER) ? 1 : 0;
+            // fewer packets than warps: idle capacity exists from the start, split on the budget alone
+            const bool crowded = round > 0 || (size_t)n_packets * 2 >= (size_t)full_grid * PK_WARPS;
+            T.sum_steps = (unsigned long long*)(n_counts + 4); T.n_done = crowded ? n_counts + 6 : nullptr;
+            if (round > 0) GB_CUDA(cudaMemsetAsync(n_counts + 4, 0, 3 * sizeof(int), st));        // per-round statistics
             if (round > 0) { T.tasks_in = lists[(round - 1) & 1]; T.n_tasks_in = n_counts + 1 + ((round - 1) & 1); }
             if (round < n_rounds - 1) {
                 T.tasks_out = lists[round & 1]; T.n_tasks_out = n_counts + 1 + (round & 1);

@@ -437,7 +437,15 @@ struct PkTasks {
     int* q_tail;              // slots reserved so far
     int* finished;            // packets + tasks finished so far; the launch is over when it equals
                               // n_packets + q_tail (every reserved slot is published and consumed)
+    // running statistics of the units that completed without being split: a unit is only worth
+    // splitting when it is much heavier than the typical one
+    unsigned long long* sum_steps;
+    int* n_done;
 };
+#ifndef PK_AVG_FACTOR_X4_V
+#define PK_AVG_FACTOR_X4_V 8
+#endif
+constexpr int PK_AVG_FACTOR_X4 = PK_AVG_FACTOR_X4_V;   // split units heavier than FACTOR/4 x the mean
 constexpr int PK_SPIN_LIMIT = 1 << 20;     // polls (up to ~4 us apart) before an idle warp gives up (error 3)
 
 // Claim `n` consecutive slots of a bounded pool; -1 if they do not fit.
@@ -623,8 +631,16 @@ trace_packet_kernel(const PkArgs P, const PkTasks T)
             // would otherwise idle: a unit is suspended once it has run `budget` steps AND the
             // ticket counter shows that no unclaimed unit is left in this launch.
             const bool may_split = T.dynamic ? level < 3 : T.tasks_out != nullptr;
-            if (may_split && guard0 - guard >= T.budget && (WIDE ? sp > 0 : top >= 0) &&
-                (T.eager || *(volatile int*)P.unit_counter >= n_units)) {
+            bool split_now = may_split && guard0 - guard >= T.budget && (WIDE ? sp > 0 : top >= 0);
+            if (split_now && !T.eager) {
+                split_now = *(volatile int*)P.unit_counter >= n_units;
+                if (split_now && T.n_done) {          // ... and this unit is heavier than most
+                    const long long nd = *(volatile int*)T.n_done;
+                    const unsigned long long ss = *(volatile unsigned long long*)T.sum_steps;
+                    if (nd > 0) split_now = 4ll * (guard0 - guard) * nd >= (long long)PK_AVG_FACTOR_X4 * (long long)ss;
+                }
+            }
+            if (split_now) {
                 // rays per child task: 8, 2, 1 by round (one launch per round) or by split level (dynamic)
                 const int child_width = T.dynamic ? (level == 0 ? 8 : level == 1 ? 2 : 1) : T.child_width;
                 const unsigned bmask0 = child_width >= 32 ? 0xffffffffu : ((1u << child_width) - 1u);
@@ -875,6 +891,7 @@ trace_packet_kernel(const PkArgs P, const PkTasks T)
         if (MODE == MODE_COUNT && lane_on) P.out_counts[ray_index] = A.count;
         if (MODE == MODE_CUMULATIVE && lane_on) P.out_cum[ray_index] = A.cum;
         if (T.dynamic && lane == 0) atomicAdd(T.finished, 1);
+        if (T.n_done && lane == 0) { atomicAdd(T.sum_steps, (unsigned long long)(guard0 - guard)); atomicAdd(T.n_done, 1); }
         if (PROF && lane == 0) {
             atomicAdd(P.prof + 0, pf_nodes); atomicAdd(P.prof + 1, pf_leaves);
             atomicAdd(P.prof + 2, pf_staged); atomicAdd(P.prof + 3, pf_kept);
