@@ -13,6 +13,11 @@ int gb_launch_morton_keys(grace_b200_ctx* ctx, const float* d_spheres4, size_t n
                           const float* d_bounds6, const float* h_bounds6, KeyT* d_keys,
                           cudaStream_t st);
 
+template <typename KeyT>
+int gb_launch_morton_keys_fused(grace_b200_ctx* ctx, const float* d_spheres4, size_t n,
+                                const float* d_bounds6, const float* h_bounds6, KeyT* d_keys,
+                                uint32_t* d_hist, int passes, float* d_copy4, cudaStream_t st);
+
 namespace {
 
 template <typename KeyT>
@@ -21,31 +26,36 @@ int morton_sort_typed(grace_b200_ctx* ctx, float* d_spheres4, size_t n, int key_
 {
     const size_t sort_ws = gb_sort_workspace_bytes(n, (int)sizeof(KeyT));
     const size_t bytes = sort_ws + gb_align(n * sizeof(KeyT)) + gb_align(n * 4) +
-                         gb_align(n * 16) + 512;
+                         gb_align(n * 16) + 512 + 8 * 256 * 4;
     char* ws = (char*)gb_workspace(ctx, bytes);
     if (!ws) return GRACE_B200_ENOMEM;
     char* p = ws + sort_ws;
     KeyT* keys = (KeyT*)p;            p += gb_align(n * sizeof(KeyT));
     uint32_t* perm = (uint32_t*)p;    p += gb_align(n * 4);
     float4* tmp = (float4*)p;         p += gb_align(n * 16);
-    float* d_bounds = (float*)p;
+    float* d_bounds = (float*)p;      p += 512;
+    uint32_t* hist = (uint32_t*)p;
+    const int sort_bits = key_bits == 30 ? 32 : 64;
+    const int passes = sort_bits / 8;
+    GB_CUDA(cudaMemsetAsync(hist, 0, (size_t)passes * 256 * 4, st));
     int rc;
+    // one pass over the spheres: keys, the digit counts of every radix pass, and the copy the
+    // final gather reads (so the gather writes the caller's array directly)
     if (h_bot3 && h_top3) {
         const float hb[6] = { h_bot3[0], h_bot3[1], h_bot3[2], h_top3[0], h_top3[1], h_top3[2] };
-        rc = gb_launch_morton_keys<KeyT>(ctx, d_spheres4, n, nullptr, hb, keys, st);
+        rc = gb_launch_morton_keys_fused<KeyT>(ctx, d_spheres4, n, nullptr, hb, keys, hist, passes, (float*)tmp, st);
     } else {
         rc = grace_b200_bounds_f4(ctx, d_spheres4, n, d_bounds, st);
         if (rc) return rc;
         // bounds kernel used the head of the arena for its partials; they are consumed
         // before the sort touches the same bytes (stream order).
-        rc = gb_launch_morton_keys<KeyT>(ctx, d_spheres4, n, d_bounds, nullptr, keys, st);
+        rc = gb_launch_morton_keys_fused<KeyT>(ctx, d_spheres4, n, d_bounds, nullptr, keys, hist, passes, (float*)tmp, st);
     }
     if (rc) return rc;
-    rc = gb_sort_pairs<KeyT>(ctx, keys, keys, perm, n, key_bits == 30 ? 32 : 64, ws, nullptr, st);
+    rc = gb_sort_pairs<KeyT>(ctx, keys, keys, perm, n, sort_bits, ws, hist, st);
     if (rc) return rc;
-    rc = gb_gather_records(d_spheres4, tmp, perm, n, 16, ctx->sm_count, st);
+    rc = gb_gather_records(tmp, d_spheres4, perm, n, 16, ctx->sm_count, st);
     if (rc) return rc;
-    GB_CUDA(cudaMemcpyAsync(d_spheres4, tmp, n * 16, cudaMemcpyDeviceToDevice, st));
     if (d_keys_out)
         GB_CUDA(cudaMemcpyAsync(d_keys_out, keys, n * sizeof(KeyT), cudaMemcpyDeviceToDevice, st));
     return GRACE_B200_OK;

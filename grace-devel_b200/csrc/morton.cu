@@ -96,18 +96,50 @@ struct Bounds6 { float v[6]; };
 
 // Bounds come either from device memory (d_bounds6 != NULL; no host round trip after
 // the bounds kernel) or by value (explicit host bounds).
-template <typename KeyT>
+// FUSED (the keys + sort entry point): the kernel also (a) counts the digits of every radix pass
+// -- the onesweep sort needs them up front and the keys are in registers here -- and (b) writes
+// a copy of the spheres for the final gather to read, so that the gather can write the sorted
+// spheres straight into the caller's array.
+template <typename KeyT, bool FUSED>
 __global__ void __launch_bounds__(256)
 morton_keys_kernel(const float4* __restrict__ s, size_t n, const float* __restrict__ d_bounds6,
-                   const Bounds6 hb, KeyT* __restrict__ keys)
+                   const Bounds6 hb, KeyT* __restrict__ keys, uint32_t* __restrict__ hist, int passes,
+                   float4* __restrict__ copy)
 {
+    __shared__ uint32_t sh[FUSED ? 8 * 256 : 1];
+    if (FUSED) {
+        for (int i = threadIdx.x; i < passes * 256; i += 256) sh[i] = 0;
+        __syncthreads();
+    }
     const float* bounds6 = d_bounds6 ? d_bounds6 : hb.v;
     const float3 bot = make_float3(bounds6[0], bounds6[1], bounds6[2]);
     const float3 scale = gb_morton_scale<KeyT>(bot, make_float3(bounds6[3], bounds6[4], bounds6[5]));
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        float4 v = gb_ld_stream_f4(s + i);
-        keys[i] = gb_morton_key<KeyT>(v, bot, scale);
+    // whole warps iterate together (match_all below needs every lane)
+    const size_t n_up = (n + 31) / 32 * 32;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_up; i += stride) {
+        const bool live = i < n;
+        KeyT k = 0;
+        if (live) {
+            const float4 v = gb_ld_stream_f4(s + i);
+            k = gb_morton_key<KeyT>(v, bot, scale);
+            keys[i] = k;
+            if (FUSED) copy[i] = v;
+        }
+        if (FUSED) {
+            for (int p = 0; p < passes; ++p) {
+                const unsigned d = (unsigned)(k >> (8 * p)) & 255u;
+                int all_same;
+                __match_all_sync(0xffffffffu, live ? d : 0x100u + (threadIdx.x & 31), &all_same);
+                if (all_same) { if ((threadIdx.x & 31) == 0) atomicAdd(&sh[p * 256 + d], 32u); }
+                else if (live) atomicAdd(&sh[p * 256 + d], 1u);
+            }
+        }
+    }
+    if (FUSED) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < passes * 256; i += 256)
+            if (sh[i]) atomicAdd(&hist[i], sh[i]);
     }
 }
 
@@ -144,11 +176,31 @@ int gb_launch_morton_keys(grace_b200_ctx* ctx, const float* d_spheres4, size_t n
     if (n == 0) return GRACE_B200_OK;
     Bounds6 hb = {};
     if (!d_bounds6) for (int i = 0; i < 6; ++i) hb.v[i] = h_bounds6[i];
-    morton_keys_kernel<KeyT><<<grid_for(ctx, n, 256 * 2, 16), 256, 0, st>>>(
-        (const float4*)d_spheres4, n, d_bounds6, hb, d_keys);
+    morton_keys_kernel<KeyT, false><<<grid_for(ctx, n, 256 * 2, 16), 256, 0, st>>>(
+        (const float4*)d_spheres4, n, d_bounds6, hb, d_keys, nullptr, 0, nullptr);
     GB_LAUNCH_CHECK();
     return GRACE_B200_OK;
 }
+
+// keys + digit histograms of all radix passes + a copy of the spheres (see the kernel)
+template <typename KeyT>
+int gb_launch_morton_keys_fused(grace_b200_ctx* ctx, const float* d_spheres4, size_t n,
+                                const float* d_bounds6, const float* h_bounds6, KeyT* d_keys,
+                                uint32_t* d_hist, int passes, float* d_copy4, cudaStream_t st)
+{
+    GB_REQUIRE(d_bounds6 || h_bounds6, GRACE_B200_EINVAL, "bounds missing");
+    if (n == 0) return GRACE_B200_OK;
+    Bounds6 hb = {};
+    if (!d_bounds6) for (int i = 0; i < 6; ++i) hb.v[i] = h_bounds6[i];
+    morton_keys_kernel<KeyT, true><<<grid_for(ctx, n, 256 * 2, 8), 256, 0, st>>>(
+        (const float4*)d_spheres4, n, d_bounds6, hb, d_keys, d_hist, passes, (float4*)d_copy4);
+    GB_LAUNCH_CHECK();
+    return GRACE_B200_OK;
+}
+template int gb_launch_morton_keys_fused<uint32_t>(grace_b200_ctx*, const float*, size_t, const float*,
+                                                   const float*, uint32_t*, uint32_t*, int, float*, cudaStream_t);
+template int gb_launch_morton_keys_fused<uint64_t>(grace_b200_ctx*, const float*, size_t, const float*,
+                                                   const float*, uint64_t*, uint32_t*, int, float*, cudaStream_t);
 template int gb_launch_morton_keys<uint32_t>(grace_b200_ctx*, const float*, size_t, const float*,
                                              const float*, uint32_t*, cudaStream_t);
 template int gb_launch_morton_keys<uint64_t>(grace_b200_ctx*, const float*, size_t, const float*,
