@@ -410,11 +410,14 @@ def run_b200(args):
                 h_in = gb.synth_gadget_spheres(n, 1234).cpu().numpy()
                 _, info = refrun.run(h_in, "gen:%d:1234:%.9g:%.9g:%.9g:%.9g" % (r, c, c, c, length),
                                      args.max_per_leaf, 30, iters=5, lists=False, timeout=600)
-                ref_ms = info["ms_cumulative"]
+                best = info.get("min_ms") or {"cumulative": info["ms_cumulative"], "hitcounts": info["ms_hitcounts"],
+                                              "keys_sort": info["ms_keys_sort"], "deltas": info["ms_deltas"],
+                                              "albvh": info["ms_albvh"]}
+                ref_ms = best["cumulative"]
+                ref_build = best["keys_sort"] + best["deltas"] + best["albvh"]
                 ref_cuda = {"value": r / ref_ms / 1e3, "unit": "Mrays/s", "ms_cumulative": ref_ms,
-                            "ms_hitcounts": info["ms_hitcounts"],
-                            "build_ms": info["ms_keys_sort"] + info["ms_deltas"] + info["ms_albvh"],
-                            "build_mparticles_s": n / (info["ms_keys_sort"] + info["ms_deltas"] + info["ms_albvh"]) / 1e3,
+                            "ms_hitcounts": best["hitcounts"], "build_ms": ref_build,
+                            "build_mparticles_s": n / ref_build / 1e3, "timing": "best of 5 iterations per stage",
                             "what": "GRACE's headers (patched only for CUDA-12 API removals, oracle/patch_ref.py) "
                                     "called through its public API on the same particles and rays, CUDA events"}
         except Exception as e:      # a baseline, never a reason to lose the bench line

@@ -81,6 +81,10 @@ int main(int argc, char** argv)
     const size_t N = h_in.size();
     Timer T;
     double t_sort = 0, t_deltas = 0, t_build = 0, t_hit = 0, t_cum = 0, t_lists = 0, t_sortd = 0, t_gen = 0;
+    // best iteration per stage: the reference allocates its temporaries inside every call, which
+    // makes single iterations noisy (a GiB-sized cudaMalloc can take longer than the kernels)
+    double m_sort = 1e30, m_deltas = 1e30, m_build = 1e30, m_hit = 1e30, m_cum = 1e30, m_lists = 1e30, m_sortd = 1e30, m_gen = 1e30;
+#define ACC(sum, mn) if (it >= 0) { sum += ms; if (ms < mn) mn = ms; }
     size_t n_leaves = 0;
 
     thrust::device_vector<float4> d_spheres;
@@ -94,13 +98,13 @@ int main(int argc, char** argv)
         T.start();
         if (key_bits == 30) grace::morton_keys30_sort_sph(d_spheres);
         else grace::morton_keys63_sort_sph(d_spheres);
-        float ms = T.stop(); if (it >= 0) t_sort += ms;
+        float ms = T.stop(); ACC(t_sort, m_sort)
         T.start();
         grace::euclidean_deltas_sph(d_spheres, d_deltas);
-        ms = T.stop(); if (it >= 0) t_deltas += ms;
+        ms = T.stop(); ACC(t_deltas, m_deltas)
         T.start();
         grace::ALBVH_sph(d_spheres, d_deltas, *tree);
-        ms = T.stop(); if (it >= 0) t_build += ms;
+        ms = T.stop(); ACC(t_build, m_build)
         n_leaves = tree->leaves.size();
     }
     dump(out, "spheres_sorted.bin", d_spheres);
@@ -123,7 +127,7 @@ int main(int argc, char** argv)
         for (int it = -1; it < iters; ++it) {
             T.start();
             grace::uniform_random_rays(d_rays, ox, oy, oz, len, seed);
-            float ms = T.stop(); if (it >= 0) t_gen += ms;
+            float ms = T.stop(); ACC(t_gen, m_gen)
         }
     } else {
         std::vector<grace::Ray> h_rays = slurp<grace::Ray>(argv[2]);
@@ -137,10 +141,10 @@ int main(int argc, char** argv)
     for (int it = -1; it < iters; ++it) {
         T.start();
         grace::trace_hitcounts_sph(d_rays, d_spheres, *tree, d_counts);
-        float ms = T.stop(); if (it >= 0) t_hit += ms;
+        float ms = T.stop(); ACC(t_hit, m_hit)
         T.start();
         grace::trace_cumulative_sph(d_rays, d_spheres, *tree, d_cum);
-        ms = T.stop(); if (it >= 0) t_cum += ms;
+        ms = T.stop(); ACC(t_cum, m_cum)
     }
     dump(out, "hitcounts.bin", d_counts);
     dump(out, "cumulative.bin", d_cum);
@@ -152,10 +156,10 @@ int main(int argc, char** argv)
         for (int it = -1; it < iters; ++it) {
             T.start();
             grace::trace_sph(d_rays, d_spheres, *tree, d_offsets, d_idx, d_integ, d_dist);
-            float ms = T.stop(); if (it >= 0) t_lists += ms;
+            float ms = T.stop(); ACC(t_lists, m_lists)
             T.start();
             grace::sort_by_distance(d_dist, d_offsets, d_idx, d_integ);
-            ms = T.stop(); if (it >= 0) t_sortd += ms;
+            ms = T.stop(); ACC(t_sortd, m_sortd)
         }
         total_hits = d_idx.size();
         dump(out, "offsets.bin", d_offsets);
@@ -168,9 +172,13 @@ int main(int argc, char** argv)
            "\"max_per_leaf\": %d, \"key_bits\": %d, \"iters\": %d, "
            "\"ms_keys_sort\": %.4f, \"ms_deltas\": %.4f, \"ms_albvh\": %.4f, \"ms_gen_rays\": %.4f, "
            "\"ms_hitcounts\": %.4f, \"ms_cumulative\": %.4f, \"ms_trace_lists\": %.4f, "
-           "\"ms_sort_by_distance\": %.4f, \"total_hits\": %zu}\n",
+           "\"ms_sort_by_distance\": %.4f, \"total_hits\": %zu, "
+           "\"min_ms\": {\"keys_sort\": %.4f, \"deltas\": %.4f, \"albvh\": %.4f, \"gen_rays\": %.4f, \"hitcounts\": %.4f, "
+           "\"cumulative\": %.4f, \"trace_lists\": %.4f, \"sort_by_distance\": %.4f}}\n",
            N, R, n_leaves, root, max_per_leaf, key_bits, iters, t_sort * k, t_deltas * k, t_build * k,
-           t_gen * k, t_hit * k, t_cum * k, t_lists * k, t_sortd * k, total_hits);
+           t_gen * k, t_hit * k, t_cum * k, t_lists * k, t_sortd * k, total_hits,
+           m_sort, m_deltas, m_build, m_gen < 1e29 ? m_gen : 0.0, m_hit, m_cum, m_lists < 1e29 ? m_lists : 0.0,
+           m_sortd < 1e29 ? m_sortd : 0.0);
     delete tree;
     return 0;
 }
