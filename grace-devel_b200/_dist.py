@@ -37,6 +37,9 @@ def padded_local_count(n_rays, world, tile=TILE):
 def take_local(rays, rank, world, tile=TILE):
     """The rank's rays, tiles concatenated in order, padded with copies of its last ray."""
     n = rays.shape[0]
+    if n % (tile * world) == 0:       # every rank owns the same number of full tiles: one strided copy
+        return rays.view(n // (tile * world), world, tile, *rays.shape[1:])[:, rank].reshape(
+            n // world, *rays.shape[1:]).contiguous()
     parts = [rays[a:b] for a, b in tiles_of_rank(n, rank, world, tile)]
     local = torch.cat(parts, 0) if parts else rays[:0]
     pad = padded_local_count(n, world, tile) - local.shape[0]
@@ -49,6 +52,9 @@ def take_local(rays, rank, world, tile=TILE):
 def scatter_back(gathered, n_rays, world, tile=TILE):
     """gathered: [world * padded_local_count] results in rank-major order -> ray order."""
     per = padded_local_count(n_rays, world, tile)
+    if n_rays % (tile * world) == 0:  # inverse of the strided copy in take_local
+        rest = tuple(gathered.shape[1:])
+        return gathered.view(world, n_rays // (tile * world), tile, *rest).transpose(0, 1).reshape(n_rays, *rest)
     out = torch.empty((n_rays,) + tuple(gathered.shape[1:]), dtype=gathered.dtype, device=gathered.device)
     for r in range(world):
         pos = r * per
