@@ -1,6 +1,6 @@
 """Dev probe: time the tree build stages at 2^24 (not product, not a test)."""
 import sys, os, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import grace_devel_b200 as gb
 lg_n = int(os.environ.get("AB_LOG2_N", "24")); n = 1 << lg_n

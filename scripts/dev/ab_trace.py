@@ -1,7 +1,7 @@
 """Dev A/B probe (not product, not a test): time the trace entry points of whichever
 libgrace_b200 build GRACE_B200_LIB selects, at the bench workload, and print an output hash."""
 import sys, os, hashlib, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import grace_devel_b200 as gb
 

@@ -1,8 +1,8 @@
 #!/bin/bash
 # Build A/B variants of libgrace_b200.so with different -D knobs into grace-devel_b200/variants/.
-# usage: scripts/ab_variants.sh name1:"-DX=1 -DY=2" name2:"..."
+# usage: scripts/dev/ab_variants.sh name1:"-DX=1 -DY=2" name2:"..."
 set -e
-cd "$(dirname "$0")/../grace-devel_b200"
+cd "$(dirname "$0")/../../grace-devel_b200"
 mkdir -p variants
 NVCC=/usr/local/cuda/bin/nvcc
 ARCH="-gencode arch=compute_100a,code=sm_100a"

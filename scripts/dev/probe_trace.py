@@ -1,6 +1,6 @@
 """Dev probe: where does the trace time go?  (not part of the product or the tests)"""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch, numpy as np
 import grace_devel_b200 as gb
 
