@@ -32,7 +32,7 @@ __all__ = [
     "uniform_random_rays", "uniform_random_rays_single_octant", "one_to_many_rays",
     "plane_parallel_random_rays", "orthographic_projection_rays", "pinhole_camera_rays",
     "healpix_rays", "synth_gadget_spheres", "exclusive_segmented_scan",
-    "weighted_exclusive_segmented_scan", "offsets_to_segments", "read_gadget", "write_gadget", "gadget_info", "context", "lib", "build_tree", "set_trace_mode", "set_trace_budget", "set_trace_dynamic", "device_error", "sharded_trace", "tiles_of_rank",
+    "weighted_exclusive_segmented_scan", "offsets_to_segments", "read_gadget", "write_gadget", "gadget_info", "context", "lib", "build_tree", "set_trace_mode", "set_trace_budget", "set_trace_dynamic", "set_trace_resume", "device_error", "sharded_trace", "tiles_of_rank",
 ]
 
 _c = ctypes
@@ -187,6 +187,10 @@ def set_trace_budget(steps, eager=False):
     """Steps before a still-running packet may be split once no unclaimed packet is left
     (eager=True: split at `steps` regardless; 0: never)."""
     _check(_sig("grace_b200_set_trace_budget", [_P, _c.c_int])(context(), int(steps) | ((1 << 30) if eager else 0)))
+
+
+def set_trace_resume(per_ray):
+    _check(_sig("grace_b200_set_trace_resume", [_P, _c.c_int])(context(), int(bool(per_ray))))
 
 
 def set_trace_dynamic(on):

@@ -299,6 +299,82 @@ __device__ __forceinline__ bool slab_hit_padded(float bx, float tx, float by, fl
     return tmax >= tmin;
 }
 
+// One ray's depth-first walk from (cur, sp): padded slab test, left child first, so primitives are
+// met in ascending index order.  Stack: RT_SMEM_DEPTH entries per lane in shared memory laid out
+// [depth][thread], deeper levels in a local array.
+struct RtRay { float lox, loy, loz, hix, hiy, hiz, ix, iy, iz; };
+template <int MODE>
+__device__ __forceinline__ void rt_walk(int cur, int sp, int* my_stack, int* lstack, const grace_b200_ray& ray, const RtRay& R,
+                                        const float4* __restrict__ spheres, const int4* __restrict__ nodes,
+                                        const int4* __restrict__ leaves, const int n_nodes, int* err_flag,
+                                        const double* s_table, int* hit_idx, float* hit_integral, float* hit_dist,
+                                        int& count, float& cum, int& cursor)
+{
+    const float lox = R.lox, loy = R.loy, loz = R.loz, hix = R.hix, hiy = R.hiy, hiz = R.hiz, ix = R.ix, iy = R.iy, iz = R.iz;
+    while (cur >= 0) {
+        // ---- inner nodes ----
+        while ((unsigned)cur < (unsigned)n_nodes) {
+            if (MODE == MODE_RAYCOST) ++cursor;      // node steps
+            const int4* np = nodes + 4 * (size_t)cur;
+            const int4 n0 = __ldg(np + 0);
+            const int4 n1 = __ldg(np + 1);
+            const int4 n2 = __ldg(np + 2);
+            const int4 n3 = __ldg(np + 3);
+            const bool hitL = slab_hit_padded(__int_as_float(n1.x), __int_as_float(n1.y),
+                                              __int_as_float(n1.z), __int_as_float(n1.w),
+                                              __int_as_float(n3.x), __int_as_float(n3.y),
+                                              lox, loy, loz, hix, hiy, hiz, ix, iy, iz, ray.length);
+            const bool hitR = slab_hit_padded(__int_as_float(n2.x), __int_as_float(n2.y),
+                                              __int_as_float(n2.z), __int_as_float(n2.w),
+                                              __int_as_float(n3.z), __int_as_float(n3.w),
+                                              lox, loy, loz, hix, hiy, hiz, ix, iy, iz, ray.length);
+            if (hitL) {
+                if (hitR) {          // push right, descend left
+                    if (sp < RT_SMEM_DEPTH) my_stack[sp * RT_THREADS] = n0.y;
+                    else if (sp < RT_SMEM_DEPTH + RT_LOCAL_DEPTH) lstack[sp - RT_SMEM_DEPTH] = n0.y;
+                    else { *err_flag = 1; }
+                    ++sp;
+                }
+                cur = n0.x;
+            } else if (hitR) {
+                cur = n0.y;
+            } else {
+                if (sp > 0) {
+                    --sp;
+                    cur = sp < RT_SMEM_DEPTH ? my_stack[sp * RT_THREADS]
+                                             : lstack[min(sp - RT_SMEM_DEPTH, RT_LOCAL_DEPTH - 1)];
+                } else cur = -1;
+            }
+        }
+        // ---- leaf ----
+        if (cur >= n_nodes) {
+            const int2 leaf = __ldg((const int2*)(leaves + (cur - n_nodes)));
+            if (MODE == MODE_RAYCOST) count += leaf.y;   // sphere tests
+            for (int i = 0; i < leaf.y && MODE != MODE_RAYCOST; ++i) {
+                const float4 s = __ldg(spheres + leaf.x + i);
+                float b2, dot;
+                if (sphere_test(s, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, ray.length, b2, dot)) {
+                    if (MODE == MODE_COUNT) {
+                        ++count;
+                    } else if (MODE == MODE_CUMULATIVE) {
+                        cum = kernel_accumulate(cum, b2, s.w, s_table);
+                    } else {
+                        hit_idx[cursor] = leaf.x + i;
+                        hit_integral[cursor] = kernel_integral(b2, s.w, s_table);
+                        hit_dist[cursor] = dot;
+                        ++cursor;
+                    }
+                }
+            }
+            if (sp > 0) {
+                --sp;
+                cur = sp < RT_SMEM_DEPTH ? my_stack[sp * RT_THREADS]
+                                         : lstack[min(sp - RT_SMEM_DEPTH, RT_LOCAL_DEPTH - 1)];
+            } else cur = -1;
+        }
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(RT_THREADS)
 trace_ray_kernel(const grace_b200_ray* __restrict__ rays, int n_packets,
@@ -338,70 +414,10 @@ trace_ray_kernel(const grace_b200_ray* __restrict__ rays, int n_packets,
         int cursor = 0;
         if (MODE == MODE_FILL) cursor = offsets[ray_index];
 
-        int sp = 0;
-        int cur = root;
-        while (cur >= 0) {
-            // ---- inner nodes ----
-            while ((unsigned)cur < (unsigned)n_nodes) {
-                if (MODE == MODE_RAYCOST) ++cursor;      // node steps
-                const int4* np = nodes + 4 * (size_t)cur;
-                const int4 n0 = __ldg(np + 0);
-                const int4 n1 = __ldg(np + 1);
-                const int4 n2 = __ldg(np + 2);
-                const int4 n3 = __ldg(np + 3);
-                const bool hitL = slab_hit_padded(__int_as_float(n1.x), __int_as_float(n1.y),
-                                                  __int_as_float(n1.z), __int_as_float(n1.w),
-                                                  __int_as_float(n3.x), __int_as_float(n3.y),
-                                                  lox, loy, loz, hix, hiy, hiz, ix, iy, iz, ray.length);
-                const bool hitR = slab_hit_padded(__int_as_float(n2.x), __int_as_float(n2.y),
-                                                  __int_as_float(n2.z), __int_as_float(n2.w),
-                                                  __int_as_float(n3.z), __int_as_float(n3.w),
-                                                  lox, loy, loz, hix, hiy, hiz, ix, iy, iz, ray.length);
-                if (hitL) {
-                    if (hitR) {          // push right, descend left
-                        if (sp < RT_SMEM_DEPTH) my_stack[sp * RT_THREADS] = n0.y;
-                        else if (sp < RT_SMEM_DEPTH + RT_LOCAL_DEPTH) lstack[sp - RT_SMEM_DEPTH] = n0.y;
-                        else { *err_flag = 1; }
-                        ++sp;
-                    }
-                    cur = n0.x;
-                } else if (hitR) {
-                    cur = n0.y;
-                } else {
-                    if (sp > 0) {
-                        --sp;
-                        cur = sp < RT_SMEM_DEPTH ? my_stack[sp * RT_THREADS]
-                                                 : lstack[min(sp - RT_SMEM_DEPTH, RT_LOCAL_DEPTH - 1)];
-                    } else cur = -1;
-                }
-            }
-            // ---- leaf ----
-            if (cur >= n_nodes) {
-                const int2 leaf = __ldg((const int2*)(leaves + (cur - n_nodes)));
-                if (MODE == MODE_RAYCOST) count += leaf.y;   // sphere tests
-                for (int i = 0; i < leaf.y && MODE != MODE_RAYCOST; ++i) {
-                    const float4 s = __ldg(spheres + leaf.x + i);
-                    float b2, dot;
-                    if (sphere_test(s, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, ray.length, b2, dot)) {
-                        if (MODE == MODE_COUNT) {
-                            ++count;
-                        } else if (MODE == MODE_CUMULATIVE) {
-                            cum = kernel_accumulate(cum, b2, s.w, s_table);
-                        } else {
-                            hit_idx[cursor] = leaf.x + i;
-                            hit_integral[cursor] = kernel_integral(b2, s.w, s_table);
-                            hit_dist[cursor] = dot;
-                            ++cursor;
-                        }
-                    }
-                }
-                if (sp > 0) {
-                    --sp;
-                    cur = sp < RT_SMEM_DEPTH ? my_stack[sp * RT_THREADS]
-                                             : lstack[min(sp - RT_SMEM_DEPTH, RT_LOCAL_DEPTH - 1)];
-                } else cur = -1;
-            }
-        }
+        RtRay R;
+        R.lox = lox; R.loy = loy; R.loz = loz; R.hix = hix; R.hiy = hiy; R.hiz = hiz; R.ix = ix; R.iy = iy; R.iz = iz;
+        rt_walk<MODE>(root, 0, my_stack, lstack, ray, R, spheres, nodes, leaves, n_nodes, err_flag, s_table, hit_idx,
+                      hit_integral, hit_dist, count, cum, cursor);
         if (MODE == MODE_COUNT) out_counts[ray_index] = count;
         if (MODE == MODE_CUMULATIVE) out_cum[ray_index] = cum;
         if (MODE == MODE_RAYCOST) { out_counts[ray_index] = count; hit_idx[ray_index] = cursor; }
@@ -409,6 +425,81 @@ trace_ray_kernel(const grace_b200_ray* __restrict__ rays, int n_packets,
 }
 
 #include "trace_packet.cuh"
+
+// ---------------------------------------------------------------------------
+// Per-ray continuation of suspended packets.
+//
+// A packet suspended by trace_packet_kernel (heavy tail of the launch) is resumed here with one
+// ray per lane: every lane rebuilds ITS OWN stack from the packet's {node, lane mask} entries and
+// walks on alone (rt_walk), so all 32 lanes stay busy whatever their rays do, where ray-subset
+// tasks of the packet kernel keep only 8, 2 or 1 lanes of a warp busy and walk the shared part
+// of the tree once per task.  Left-first depth-first order is kept, so every ray still meets
+// its primitives in ascending index order: results are bit-identical.
+// ---------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(RT_THREADS)
+trace_ray_resume_kernel(const PkArgs P, const int* __restrict__ records, const int* __restrict__ n_records_ptr,
+                        const int records_cap)
+{
+    __shared__ double s_table[52];
+    __shared__ int s_stack[RT_SMEM_DEPTH * RT_THREADS];
+    const int lane = threadIdx.x & 31;
+    if (MODE == MODE_CUMULATIVE || MODE == MODE_FILL) {
+        for (int i = threadIdx.x; i < N_TABLE; i += RT_THREADS) s_table[i] = c_kernel_table[i];
+        __syncthreads();
+    }
+    int* my_stack = s_stack + threadIdx.x;
+    int lstack[RT_LOCAL_DEPTH];
+    const int n_rec = min(__ldg(n_records_ptr), records_cap);
+    for (;;) {
+        int unit = 0;
+        if (lane == 0) unit = atomicAdd(P.unit_counter, 1);
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        if (unit >= n_rec) break;
+        const int* rec = records + (size_t)unit * PK_REC_WORDS;
+        const int packet = rec[0];
+        const unsigned subset = (unsigned)rec[1];
+        const int sp_pk = rec[2], top = rec[3];
+        const unsigned top_mask = (unsigned)rec[4];
+        const bool mine = (subset >> lane) & 1u;
+        const int ray_index = packet * 32 + lane;
+        const grace_b200_ray ray = P.rays[ray_index];
+        RtRay R;
+        R.ix = __fdiv_rn(1.0f, ray.dx); R.iy = __fdiv_rn(1.0f, ray.dy); R.iz = __fdiv_rn(1.0f, ray.dz);
+        const float pad = 64.0f * 5.9604645e-8f * (fabsf(ray.ox) + fabsf(ray.oy) + fabsf(ray.oz) + fabsf(ray.length));
+        R.lox = ray.ox + pad; R.loy = ray.oy + pad; R.loz = ray.oz + pad;
+        R.hix = ray.ox - pad; R.hiy = ray.oy - pad; R.hiz = ray.oz - pad;
+        float cum = __int_as_float(rec[8 + 2 * PK_STACK + lane]);
+        int count = rec[8 + 2 * PK_STACK + 32 + lane];
+        int cursor = rec[8 + 2 * PK_STACK + 64 + lane];
+        // this lane's stack: the packet's entries (bottom to top) whose mask holds the lane
+        int sp = 0;
+        const int2* pk_stack = (const int2*)(rec + 8);
+        for (int i = 0; i < sp_pk; ++i) {
+            const int2 e = pk_stack[i];
+            if (mine && (((unsigned)e.y >> lane) & 1u)) {
+                if (sp < RT_SMEM_DEPTH) my_stack[sp * RT_THREADS] = e.x;
+                else if (sp < RT_SMEM_DEPTH + RT_LOCAL_DEPTH) lstack[sp - RT_SMEM_DEPTH] = e.x;
+                else *P.err_flag = 1;
+                ++sp;
+            }
+        }
+        int cur = -1;
+        if (mine) {
+            if (top >= 0 && ((top_mask >> lane) & 1u)) cur = top;
+            else if (sp > 0) {
+                --sp;
+                cur = sp < RT_SMEM_DEPTH ? my_stack[sp * RT_THREADS] : lstack[min(sp - RT_SMEM_DEPTH, RT_LOCAL_DEPTH - 1)];
+            }
+        }
+        rt_walk<MODE>(cur, sp, my_stack, lstack, ray, R, P.spheres, P.nodes, P.leaves, P.n_nodes, P.err_flag, s_table,
+                      P.hit_idx, P.hit_integral, P.hit_dist, count, cum, cursor);
+        if (mine) {
+            if (MODE == MODE_COUNT) P.out_counts[ray_index] = count;
+            if (MODE == MODE_CUMULATIVE) P.out_cum[ray_index] = cum;
+        }
+    }
+}
 
 size_t trace_smem_bytes(int max_per_leaf)
 {
@@ -481,6 +572,27 @@ int launch_packet(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, int n_packe
         GB_CUDA(cudaMemsetAsync(T.queue, 0xff, (size_t)T.queue_cap * 8, st));    // slot.x = -1: not published
         GB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
         kernel<<<full_grid, PK_THREADS, psmem, st>>>(P, T);
+        GB_LAUNCH_CHECK();
+        return GRACE_B200_OK;
+    }
+    if (split && ctx->trace_resume_per_ray && !wide) {
+        // Round 0: packets; the heavy ones still running when the queue drains are suspended whole.
+        // Round 1: their rays continue one per lane (trace_ray_resume_kernel).
+        PkTasks T = {};
+        T.records = records; T.n_records = n_counts; T.records_cap = records_cap; T.tasks_cap = tasks_cap;
+        T.budget = ctx->trace_budget & 0x3fffffff;
+        T.eager = (ctx->trace_budget & GRACE_B200_BUDGET_EAGER) ? 1 : 0;
+        T.tasks_out = lists[0]; T.n_tasks_out = n_counts + 1; T.child_width = 32;
+        const bool crowded = (size_t)n_packets * 2 >= (size_t)full_grid * PK_WARPS;
+        T.sum_steps = (unsigned long long*)(n_counts + 4); T.n_done = crowded ? n_counts + 6 : nullptr;
+        GB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
+        kernel<<<blocks, PK_THREADS, psmem, st>>>(P, T);
+        GB_LAUNCH_CHECK();
+        int rper = 0;
+        GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&rper, trace_ray_resume_kernel<KMODE>, RT_THREADS, 0));
+        if (rper < 1) rper = 1;
+        GB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
+        trace_ray_resume_kernel<KMODE><<<ctx->sm_count * rper, RT_THREADS, 0, st>>>(P, records, n_counts, records_cap);
         GB_LAUNCH_CHECK();
         return GRACE_B200_OK;
     }
@@ -593,6 +705,13 @@ int grace_b200_set_trace_budget(grace_b200_ctx* ctx, int steps)
 {
     GB_REQUIRE(ctx && steps >= 0, GRACE_B200_EINVAL, "bad argument");
     ctx->trace_budget = steps;
+    return GRACE_B200_OK;
+}
+
+int grace_b200_set_trace_resume(grace_b200_ctx* ctx, int per_ray)
+{
+    GB_REQUIRE(ctx, GRACE_B200_EINVAL, "ctx is NULL");
+    ctx->trace_resume_per_ray = per_ray ? 1 : 0;
     return GRACE_B200_OK;
 }
 

@@ -649,7 +649,10 @@ trace_packet_kernel(const PkArgs P, const PkTasks T)
                     if (subset & (bmask0 << (b * child_width))) blocks |= 1u << b;
                 const int nchild = __popc(blocks);
                 int rslot = -1, tslot = -1;
-                if (nchild > 1 && lane == 0) {
+                if (child_width >= 32) {       // handed over whole: the per-ray kernel resumes all its rays
+                    if (lane == 0) rslot = pk_reserve(T.n_records, 1, T.records_cap);
+                    tslot = 0;
+                } else if (nchild > 1 && lane == 0) {
                     // Reserve with compare-and-swap: a counter must never be visible above its
                     // final value (an add-then-undo would let another warp claim slots past it).
                     if (T.dynamic) {
@@ -683,7 +686,7 @@ trace_packet_kernel(const PkArgs P, const PkTasks T)
                         __threadfence();
                         __syncwarp();
                     }
-                    if (lane < nchild) {      // lane c publishes the c-th non-empty block
+                    if (child_width < 32 && lane < nchild) {      // lane c publishes the c-th non-empty block
                         unsigned bb = blocks;
                         for (int c = 0; c < lane; ++c) bb &= bb - 1;
                         const int b = __ffs(bb) - 1;

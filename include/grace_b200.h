@@ -186,6 +186,9 @@ int grace_b200_set_trace_budget(grace_b200_ctx* ctx, int steps);
 /* Where suspended traversals are resumed: 0 = in follow-up launches, one per split level (tasks
  * of 8, 2, 1 rays); 1 = inside the same launch, from a queue the idle warps drain. */
 int grace_b200_set_trace_dynamic(grace_b200_ctx* ctx, int on);
+/* How suspended packets continue: 0 = as tasks over subsets of 8, 2, 1 of their rays (packet
+ * kernel); 1 = whole, one ray per lane, each lane with its own stack (per-ray kernel). */
+int grace_b200_set_trace_resume(grace_b200_ctx* ctx, int per_ray);
 /* Device-side error flag of the last trace launch: 0 = none, 1 = traversal stack overflow
  * (the reference asserts on this only under GRACE_DEBUG, bintree_trace.cuh:162-164),
  * 2 = traversal did not terminate within 2*n_nodes steps (malformed tree).

@@ -30,7 +30,8 @@ mode = os.environ.get("AB_MODE", "packet")
 gb.set_trace_mode(mode)
 if os.environ.get("AB_BUDGET"): gb.set_trace_budget(int(os.environ["AB_BUDGET"]))
 if os.environ.get("AB_DYNAMIC"): gb.set_trace_dynamic(int(os.environ["AB_DYNAMIC"]))
-res = {"lib": os.environ.get("GRACE_B200_LIB", "default").split("_")[-1], "mode": mode, "budget": os.environ.get("AB_BUDGET"), "dyn": os.environ.get("AB_DYNAMIC"), "lr": lg_r}
+if os.environ.get("AB_RESUME"): gb.set_trace_resume(int(os.environ["AB_RESUME"]))
+res = {"lib": os.environ.get("GRACE_B200_LIB", "default").split("_")[-1], "mode": mode, "budget": os.environ.get("AB_BUDGET"), "dyn": os.environ.get("AB_DYNAMIC"), "resume": os.environ.get("AB_RESUME"), "lr": lg_r}
 res["hitcounts_ms"] = timeit(lambda: gb.trace_hitcounts_sph(rays, s, tree, counts))
 res["cumulative_ms"] = timeit(lambda: gb.trace_cumulative_sph(rays, s, tree, out))
 res["counts_sha"] = hashlib.sha1(counts.cpu().numpy().tobytes()).hexdigest()[:12]

@@ -266,7 +266,7 @@ def test_hit_lists_and_sort(gb, orc, scene):
     assert np.array_equal(host(integ).view(np.uint32), sg.view(np.uint32))
 
 
-@pytest.mark.parametrize("dynamic", [False, True])
+@pytest.mark.parametrize("dynamic", [False, True, "per_ray"])
 @pytest.mark.parametrize("budget", [8, 100, 1000])
 def test_packet_splitting_is_exact(gb, orc, scene, budget, dynamic, trace_mode):
     """Over-budget packets are suspended and resumed as ray-subset tasks; with a tiny
@@ -275,7 +275,10 @@ def test_packet_splitting_is_exact(gb, orc, scene, budget, dynamic, trace_mode):
         pytest.skip("splitting exists only in the production packet schedule")
     d_s, tree, hs, htree, rays = scene
     gb.set_trace_budget(budget, eager=True)
-    gb.set_trace_dynamic(dynamic)       # resumed in follow-up launches, or from a queue inside the launch
+    # resumed as ray-subset tasks in follow-up launches, from a queue inside the launch, or whole
+    # with one ray per lane (per-ray kernel)
+    gb.set_trace_dynamic(dynamic is True)
+    gb.set_trace_resume(dynamic == "per_ray")
     try:
         d_rays = dev(rays)
         cnt = torch.empty(len(rays), dtype=torch.int32, device="cuda")
@@ -296,6 +299,7 @@ def test_packet_splitting_is_exact(gb, orc, scene, budget, dynamic, trace_mode):
     finally:
         gb.set_trace_budget(2048)
         gb.set_trace_dynamic(False)
+        gb.set_trace_resume(False)
 
 
 def test_axis_aligned_and_degenerate_directions(gb, orc, scene):
