@@ -128,7 +128,6 @@ public:
     __device__ void operator()(const int, const Ray&, RayData& ray_data, const int sphere_idx, const Real4& sphere,
                                const int, const gpu::BoundIter<char> smem_iter)
     {
-        typedef typename Real4ToRealMapper<Real4>::type Real;
         gpu::BoundIter<double> Wk_lookup = smem_iter;
         Real ir = 1.f / sphere.w;
         Real b = (N_table - 1) * (sqrt(ray_data.b2) * ir);

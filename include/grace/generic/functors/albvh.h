@@ -10,6 +10,17 @@
 
 namespace grace {
 
+namespace detail {
+GRACE_HOST_DEVICE float delta_infinity()
+{
+#ifdef __CUDA_ARCH__
+    return __int_as_float(0x7f800000);
+#else
+    return std::numeric_limits<float>::infinity();
+#endif
+}
+} // namespace detail
+
 struct DeltaXOR {
     GRACE_HOST_DEVICE uinteger32 operator()(const int i, const uinteger32* keys, const size_t n) const
     {
@@ -27,7 +38,7 @@ template <typename PrimitiveIter, typename CentroidFunc>
 struct DeltaEuclidean {
     GRACE_HOST_DEVICE float operator()(const int i, PrimitiveIter prims, const size_t n) const
     {
-        if (i < 0 || (size_t)i + 1 >= n) return std::numeric_limits<float>::infinity();
+        if (i < 0 || (size_t)i + 1 >= n) return detail::delta_infinity();
         typename std::iterator_traits<PrimitiveIter>::value_type a = prims[i], b = prims[i + 1];
         return (a.x - b.x) * (a.x - b.x) + (a.y - b.y) * (a.y - b.y) + (a.z - b.z) * (a.z - b.z);
     }
@@ -37,7 +48,7 @@ template <typename PrimitiveIter, typename AABBFunc>
 struct DeltaSurfaceArea {
     GRACE_HOST_DEVICE float operator()(const int i, PrimitiveIter prims, const size_t n) const
     {
-        if (i < 0 || (size_t)i + 1 >= n) return std::numeric_limits<float>::infinity();
+        if (i < 0 || (size_t)i + 1 >= n) return detail::delta_infinity();
         float3 bi, ti, bj, tj;
         AABBFunc()(prims[i], &bi, &ti);
         AABBFunc()(prims[i + 1], &bj, &tj);

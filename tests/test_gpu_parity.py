@@ -326,6 +326,39 @@ def test_axis_aligned_and_degenerate_directions(gb, orc, scene):
     assert np.array_equal(host(cum).view(np.uint32), orc.brute_cumulative(rays, hs).view(np.uint32))
 
 
+def test_trace_empty_and_degenerate_inputs(gb, orc, scene):
+    """No rays is a no-op; zero-length rays hit nothing; rays with NaN/inf components must not
+    hang or fault and must not disturb their packet neighbours (sphere_hit's comparisons are all
+    false for NaN, generic/intersect.h:38-48)."""
+    d_s, tree, hs, htree, rays = scene
+    empty = torch.empty((0, 7), dtype=torch.float32, device="cuda")
+    gb.trace_hitcounts_sph(empty, d_s, tree, torch.empty(0, dtype=torch.int32, device="cuda"))
+    gb.trace_cumulative_sph(empty, d_s, tree, torch.empty(0, dtype=torch.float32, device="cuda"))
+    off = torch.empty(0, dtype=torch.int32, device="cuda")
+    idx, integ, dist = gb.trace_sph(empty, d_s, tree, off)
+    assert idx.numel() == 0
+    r = rays[:64].copy()
+    r[0:8, 6] = 0.0                       # zero length
+    r[8, 0] = np.nan                      # NaN direction component
+    r[9, 3] = np.nan                      # NaN origin
+    r[10, 6] = np.inf                     # infinite length
+    r[11, :3] = 0.0                       # null direction
+    d_r = dev(r)
+    cnt = torch.empty(64, dtype=torch.int32, device="cuda")
+    cum = torch.empty(64, dtype=torch.float32, device="cuda")
+    gb.trace_hitcounts_sph(d_r, d_s, tree, cnt)
+    gb.trace_cumulative_sph(d_r, d_s, tree, cum)
+    torch.cuda.synchronize()
+    assert gb.device_error() == 0
+    c = host(cnt)
+    assert (c[0:8] == 0).all() and c[8] == 0 and c[9] == 0
+    ok = np.ones(64, bool)
+    ok[8:12] = False                      # the oracle's own treatment of NaN/inf rays is not the contract
+    want = orc.brute_hitcounts(r, hs)
+    assert np.array_equal(c[ok], want[ok])
+    assert np.array_equal(host(cum)[ok].view(np.uint32), orc.brute_cumulative(r, hs)[ok].view(np.uint32))
+
+
 def test_hit_lists_with_sentinels(gb, orc, scene):
     d_s, tree, hs, htree, rays = scene
     rays = rays[:256]
