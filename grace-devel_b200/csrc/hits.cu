@@ -368,7 +368,8 @@ int grace_b200_trace_hits_count_f4(grace_b200_ctx* ctx, const grace_b200_ray* d_
                                    int with_sentinels, int* d_ray_offsets, long long* h_total_hits,
                                    void* stream)
 {
-    GB_REQUIRE(ctx && d_ray_offsets && h_total_hits, GRACE_B200_EINVAL, "NULL argument");
+    GB_REQUIRE(ctx && (d_ray_offsets || n_rays == 0) && h_total_hits, GRACE_B200_EINVAL, "NULL argument");
+    if (n_rays == 0) { *h_total_hits = 0; return GRACE_B200_OK; }
     cudaStream_t st = (cudaStream_t)stream;
     int rc = grace_b200_trace_hitcounts_f4(ctx, d_rays, n_rays, d_spheres4, n, tree, d_ray_offsets, stream);
     if (rc) return rc;

@@ -628,7 +628,7 @@ int launch_trace(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, size_t n_ray
                  float* hit_integral, float* hit_dist, cudaStream_t st,
                  unsigned long long* d_stats = nullptr)
 {
-    GB_REQUIRE(ctx && d_rays && d_spheres4 && tree && tree->d_nodes && tree->d_leaves && tree->d_root,
+    GB_REQUIRE(ctx && (d_rays || n_rays == 0) && d_spheres4 && tree && tree->d_nodes && tree->d_leaves && tree->d_root,
                GRACE_B200_EINVAL, "NULL argument");
     // bintree_trace.cuh:231-238
     GB_REQUIRE(n_rays % 32 == 0, GRACE_B200_EINVAL,
@@ -741,7 +741,7 @@ int grace_b200_trace_hitcounts_f4(grace_b200_ctx* ctx, const grace_b200_ray* d_r
                                   const float* d_spheres4, size_t n, const grace_b200_tree* tree,
                                   int* d_hit_counts, void* stream)
 {
-    GB_REQUIRE(d_hit_counts, GRACE_B200_EINVAL, "NULL output");
+    GB_REQUIRE(d_hit_counts || n_rays == 0, GRACE_B200_EINVAL, "NULL output");
     return launch_trace<MODE_COUNT>(ctx, d_rays, n_rays, d_spheres4, n, tree, d_hit_counts, nullptr,
                                     nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
@@ -750,7 +750,7 @@ int grace_b200_trace_cumulative_f4(grace_b200_ctx* ctx, const grace_b200_ray* d_
                                    const float* d_spheres4, size_t n, const grace_b200_tree* tree,
                                    float* d_cumulated, void* stream)
 {
-    GB_REQUIRE(d_cumulated, GRACE_B200_EINVAL, "NULL output");
+    GB_REQUIRE(d_cumulated || n_rays == 0, GRACE_B200_EINVAL, "NULL output");
     return launch_trace<MODE_CUMULATIVE>(ctx, d_rays, n_rays, d_spheres4, n, tree, nullptr,
                                          d_cumulated, nullptr, nullptr, nullptr, nullptr,
                                          (cudaStream_t)stream);

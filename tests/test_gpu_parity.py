@@ -328,8 +328,9 @@ def test_axis_aligned_and_degenerate_directions(gb, orc, scene):
 
 def test_trace_empty_and_degenerate_inputs(gb, orc, scene):
     """No rays is a no-op; zero-length rays hit nothing; rays with NaN/inf components must not
-    hang or fault and must not disturb their packet neighbours (sphere_hit's comparisons are all
-    false for NaN, generic/intersect.h:38-48)."""
+    hang or fault and must not disturb their packet neighbours.  (What a NaN ray itself "hits" is
+    not a contract: every comparison of sphere_hit is false for NaN, so it accepts whatever it is
+    tested against, generic/intersect.h:38-48, and that depends on the schedule.)"""
     d_s, tree, hs, htree, rays = scene
     empty = torch.empty((0, 7), dtype=torch.float32, device="cuda")
     gb.trace_hitcounts_sph(empty, d_s, tree, torch.empty(0, dtype=torch.int32, device="cuda"))
@@ -351,7 +352,7 @@ def test_trace_empty_and_degenerate_inputs(gb, orc, scene):
     torch.cuda.synchronize()
     assert gb.device_error() == 0
     c = host(cnt)
-    assert (c[0:8] == 0).all() and c[8] == 0 and c[9] == 0
+    assert (c[0:8] == 0).all()
     ok = np.ones(64, bool)
     ok[8:12] = False                      # the oracle's own treatment of NaN/inf rays is not the contract
     want = orc.brute_hitcounts(r, hs)
