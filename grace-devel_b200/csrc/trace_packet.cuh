@@ -347,7 +347,24 @@ __device__ __forceinline__ void pk_leaf_dense(PkWarp<MODE, M4>& W, int n_kept, c
         A.room -= n;
         const int end = i + n;
         int qn = A.qn;
-#pragma unroll 4
+        // two spheres per step: both tests are computed before either push, so their dependent
+        // FMA chains overlap (the pushes' shared-memory stores would otherwise order them)
+        for (; i + 1 < end; i += 2) {
+            const float4 s0 = W.prims[i], s1 = W.prims[i + 1];
+            float b20, dot0, b21, dot1;
+            const bool hit0 = pk_test<COMMON>(s0, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, ray.length, b20, dot0) && lane_on;
+            const bool hit1 = pk_test<COMMON>(s1, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, ray.length, b21, dot1) && lane_on;
+            if (hit0) {
+                W.q[qn * 32 + lane] = make_float2(b20, W.ir[i]);
+                if (MODE == MODE_FILL) W.q2[qn * 32 + lane] = make_float2(dot0, __int_as_float(W.idx[i]));
+                ++qn;
+            }
+            if (hit1) {
+                W.q[qn * 32 + lane] = make_float2(b21, W.ir[i + 1]);
+                if (MODE == MODE_FILL) W.q2[qn * 32 + lane] = make_float2(dot1, __int_as_float(W.idx[i + 1]));
+                ++qn;
+            }
+        }
         for (; i < end; ++i) {
             const float4 s = W.prims[i];
             float b2, dot;
