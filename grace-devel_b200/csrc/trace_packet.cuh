@@ -327,6 +327,9 @@ __device__ __forceinline__ bool pk_test(const float4 s, float ox, float oy, floa
 // lane's FIFO; the loop body has no vote and no branch: it runs for `room` spheres, the
 // number of pushes every lane's FIFO is known to have space for, and only then looks at the
 // fill levels again.
+#ifndef PK_PAIRS_OK
+#define PK_PAIRS_OK(mode) ((mode) == MODE_CUMULATIVE)      // hit lists carry twice the per-hit state: no gain there
+#endif
 template <int MODE, int M4, bool COMMON>
 __device__ __forceinline__ void pk_leaf_dense(PkWarp<MODE, M4>& W, int n_kept, const grace_b200_ray& ray,
                                               int lane, unsigned lt, bool lane_on, PkAcc& A, const double2* table)
@@ -349,7 +352,7 @@ __device__ __forceinline__ void pk_leaf_dense(PkWarp<MODE, M4>& W, int n_kept, c
         int qn = A.qn;
         // two spheres per step: both tests are computed before either push, so their dependent
         // FMA chains overlap (the pushes' shared-memory stores would otherwise order them)
-        for (; i + 1 < end; i += 2) {
+        for (; PK_PAIRS_OK(MODE) && i + 1 < end; i += 2) {
             const float4 s0 = W.prims[i], s1 = W.prims[i + 1];
             float b20, dot0, b21, dot1;
             const bool hit0 = pk_test<COMMON>(s0, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, ray.length, b20, dot0) && lane_on;
