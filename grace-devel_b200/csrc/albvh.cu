@@ -280,13 +280,64 @@ leaves_kernel(const T* __restrict__ deltas_shifted, int n, int mpl,
 // ---------------------------------------------------------------------------
 // nodes
 // ---------------------------------------------------------------------------
-// A warp owns 32 consecutive leaves.  (1) Leaf AABBs: one lane per leaf.  (2) Every node whose whole range lies inside the warp's 32 leaves is built in
-// registers: lane (l - w) holds the finished subtree [l, r]; in each round a left child
-// fetches its right sibling's state by shuffle when that sibling is finished too, writes the
-// parent's complete 64-byte record (the reference layout, cuda/nodes.h:21-36) and becomes the
-// parent.  No atomics, no fences: ~90 % of the nodes.  (3) The subtrees left over climb the
-// Karras/Apetrei way through one arrival counter per node.
+// nodes_kernel builds the inner nodes bottom-up in three stages of decreasing locality:
+//  (1) one lane per leaf AABB;
+//  (2) merging in registers: the finished subtrees a warp holds tile a range of leaves in order,
+//      one per active lane.  [l, r] is the right child of node l-1 if delta(l-1) < delta(r), else
+//      the left child of node r (ties go right), so a LEFT child whose next subtree is a RIGHT
+//      child has found its sibling (both name node r): the left lane fetches the sibling's state
+//      by shuffle, writes the parent's complete 64-byte record (the reference layout,
+//      cuda/nodes.h:21-36) and becomes the parent; the right lane retires.  Rounds repeat until
+//      nothing merges.  Applied first to the 32 leaves of each warp, then -- through shared
+//      memory -- to what the 8 warps of the block have left (256 consecutive leaves).  No atomics,
+//      no fences: ~99 % of the nodes;
+//  (3) the few subtrees a block cannot finish climb Karras/Apetrei-style through one arrival
+//      counter per node (fence + atomic per level: this was 2/3 of the kernel when every warp's
+//      leftovers went straight to it).
 constexpr int ND_THREADS = 256;
+constexpr int ND_WARPS = ND_THREADS / 32;
+
+template <typename T>
+struct NdSub {            // a finished subtree
+    int l, r, cur;        // leaf range, node index (>= n_nodes: leaf)
+    T dl, dr;             // delta(l - 1), delta(r)
+    float bx, by, bz, tx, ty, tz;
+};
+
+// One warp merges the subtrees its active lanes hold (in order, tiling a leaf range).
+template <typename T>
+__device__ __forceinline__ void nd_merge_rounds(NdSub<T>& S, bool& active, int lane, int4* nodes)
+{
+    for (;;) {
+        const bool right_child = S.dl < S.dr;
+        const unsigned amask = __ballot_sync(0xffffffffu, active);
+        const unsigned higher = lane == 31 ? 0u : (amask & ~((2u << lane) - 1u));
+        const int nxt = higher ? __ffs(higher) - 1 : -1;
+        const int sl = nxt >= 0 ? nxt : lane;
+        const bool s_right = __shfl_sync(0xffffffffu, (int)right_child, sl);
+        const int s_r = __shfl_sync(0xffffffffu, S.r, sl);
+        const int s_cur = __shfl_sync(0xffffffffu, S.cur, sl);
+        const T s_dr = __shfl_sync(0xffffffffu, S.dr, sl);
+        const float sbx = __shfl_sync(0xffffffffu, S.bx, sl), sby = __shfl_sync(0xffffffffu, S.by, sl),
+                    sbz = __shfl_sync(0xffffffffu, S.bz, sl), stx = __shfl_sync(0xffffffffu, S.tx, sl),
+                    sty = __shfl_sync(0xffffffffu, S.ty, sl), stz = __shfl_sync(0xffffffffu, S.tz, sl);
+        const bool merge = active && !right_child && nxt >= 0 && s_right;
+        const unsigned absorbed = __reduce_or_sync(0xffffffffu, merge ? (1u << sl) : 0u);
+        if (absorbed == 0u) break;
+        if (merge) {
+            const int parent = S.r;
+            int4* np = nodes + 4 * (size_t)parent;
+            np[0] = make_int4(S.cur, s_cur, S.l, s_r);
+            np[1] = make_int4(__float_as_int(S.bx), __float_as_int(S.tx), __float_as_int(S.by), __float_as_int(S.ty));
+            np[2] = make_int4(__float_as_int(sbx), __float_as_int(stx), __float_as_int(sby), __float_as_int(sty));
+            np[3] = make_int4(__float_as_int(S.bz), __float_as_int(S.tz), __float_as_int(sbz), __float_as_int(stz));
+            S.cur = parent; S.r = s_r; S.dr = s_dr;
+            S.bx = fminf(S.bx, sbx); S.by = fminf(S.by, sby); S.bz = fminf(S.bz, sbz);
+            S.tx = fmaxf(S.tx, stx); S.ty = fmaxf(S.ty, sty); S.tz = fmaxf(S.tz, stz);
+        }
+        if ((absorbed >> lane) & 1u) active = false;
+    }
+}
 
 // FROM_AABB: `spheres` holds two float4 per primitive, {bx,by,bz,-} {tx,ty,tz,-}: boxes a user's
 // AABB functor produced (generic primitives), instead of {x,y,z,h} spheres.
@@ -296,20 +347,24 @@ nodes_kernel(const float4* __restrict__ spheres, const int4* __restrict__ leaves
              const int* __restrict__ n_leaves_ptr, const T* __restrict__ ld_shifted,
              int4* nodes, unsigned* flags, int* __restrict__ root)
 {
+    __shared__ NdSub<T> s_sub[ND_THREADS];
+    __shared__ int s_cnt[ND_WARPS];
+    __shared__ int s_m;
     const int L = *n_leaves_ptr;
     const int n_nodes = L - 1;
-    const int lane = threadIdx.x & 31;
-    const int warps_total = gridDim.x * (ND_THREADS / 32);
-    // w = first leaf of the warp's window
-    for (int w = (blockIdx.x * (ND_THREADS / 32) + (threadIdx.x >> 5)) * 32; w < L; w += warps_total * 32) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // the block's window: ND_THREADS consecutive leaves, 32 per warp (block-uniform loop: barriers inside)
+    for (int B = blockIdx.x * ND_THREADS; B < L; B += gridDim.x * ND_THREADS) {
+    const int w = B + warp * 32;
     const int leaf = w + lane;
     bool active = leaf < L;
 
     // ---- (1) leaf boxes ----
     int2 lf = make_int2(0, 0);
     if (active) lf = __ldg((const int2*)(leaves + leaf));
-    float bx = CUDART_INF_F, by = CUDART_INF_F, bz = CUDART_INF_F;
-    float tx = -CUDART_INF_F, ty = -CUDART_INF_F, tz = -CUDART_INF_F;
+    NdSub<T> S;
+    S.bx = S.by = S.bz = CUDART_INF_F;
+    S.tx = S.ty = S.tz = -CUDART_INF_F;
     // every lane folds its own leaf: the loads of one lane are independent (deep unrolling keeps
     // several 16-byte loads in flight) and the warp's leaves are contiguous in memory, so all
     // the lines it touches are consumed in full
@@ -317,63 +372,67 @@ nodes_kernel(const float4* __restrict__ spheres, const int4* __restrict__ leaves
     for (int i = 0; i < lf.y; ++i) {
         if (FROM_AABB) {
             const float4 b = __ldg(spheres + 2 * (size_t)(lf.x + i)), t = __ldg(spheres + 2 * (size_t)(lf.x + i) + 1);
-            bx = fminf(bx, b.x); by = fminf(by, b.y); bz = fminf(bz, b.z);
-            tx = fmaxf(tx, t.x); ty = fmaxf(ty, t.y); tz = fmaxf(tz, t.z);
+            S.bx = fminf(S.bx, b.x); S.by = fminf(S.by, b.y); S.bz = fminf(S.bz, b.z);
+            S.tx = fmaxf(S.tx, t.x); S.ty = fmaxf(S.ty, t.y); S.tz = fmaxf(S.tz, t.z);
         } else {
             const float4 s = __ldg(spheres + lf.x + i);
             // AABBSphere, generic/functors/aabb.h:9-26: centre -/+ h, one FADD each
-            bx = fminf(bx, __fsub_rn(s.x, s.w)); tx = fmaxf(tx, __fadd_rn(s.x, s.w));
-            by = fminf(by, __fsub_rn(s.y, s.w)); ty = fmaxf(ty, __fadd_rn(s.y, s.w));
-            bz = fminf(bz, __fsub_rn(s.z, s.w)); tz = fmaxf(tz, __fadd_rn(s.z, s.w));
+            S.bx = fminf(S.bx, __fsub_rn(s.x, s.w)); S.tx = fmaxf(S.tx, __fadd_rn(s.x, s.w));
+            S.by = fminf(S.by, __fsub_rn(s.y, s.w)); S.ty = fmaxf(S.ty, __fadd_rn(s.y, s.w));
+            S.bz = fminf(S.bz, __fsub_rn(s.z, s.w)); S.tz = fmaxf(S.tz, __fadd_rn(s.z, s.w));
         }
     }
 
-    // ---- (2) nodes inside the warp's window ----
-    // dlo = delta(w + lane - 1); dtop = delta(w + 31) (needed by subtrees ending at the last leaf)
-    const T dlo = ld_shifted[min(leaf, L)];
-    const T dtop = ld_shifted[min(w + 32, L)];
-    int cur = leaf + n_nodes;          // child index >= n_nodes marks a leaf
-    int l = leaf, r = leaf;
-    bool right_child = false;
-    int parent = -1;
-    for (;;) {
-        // parent rule: [l, r] is the right child of node l-1 if delta(l-1) < delta(r), else the
-        // left child of node r
-        const T dl = __shfl_sync(0xffffffffu, dlo, (l - w) & 31);
-        T dr = __shfl_sync(0xffffffffu, dlo, (r - w + 1) & 31);
-        if (r - w + 1 >= 32) dr = dtop;
-        right_child = dl < dr;
-        parent = right_child ? l - 1 : r;
-        const bool is_root = active && (parent < 0 || parent >= n_nodes);
-        if (is_root) { *root = cur; active = false; }
-        // a left child looks at the lane holding the subtree that starts at r + 1
-        const int sib = r + 1 - w;
-        const bool sib_in = active && !right_child && sib < 32;
-        const int sl = sib_in ? sib : lane;
-        const bool s_active = __shfl_sync(0xffffffffu, (int)active, sl);
-        const bool s_right = __shfl_sync(0xffffffffu, (int)right_child, sl);
-        const int s_parent = __shfl_sync(0xffffffffu, parent, sl);
-        const int s_r = __shfl_sync(0xffffffffu, r, sl);
-        const int s_cur = __shfl_sync(0xffffffffu, cur, sl);
-        const float sbx = __shfl_sync(0xffffffffu, bx, sl), sby = __shfl_sync(0xffffffffu, by, sl),
-                    sbz = __shfl_sync(0xffffffffu, bz, sl), stx = __shfl_sync(0xffffffffu, tx, sl),
-                    sty = __shfl_sync(0xffffffffu, ty, sl), stz = __shfl_sync(0xffffffffu, tz, sl);
-        const bool merge = sib_in && s_active && s_right && s_parent == parent;
-        const unsigned absorbed = __reduce_or_sync(0xffffffffu, merge ? (1u << sib) : 0u);
-        if (absorbed == 0u) break;
-        if (merge) {
-            int4* np = nodes + 4 * (size_t)parent;
-            np[0] = make_int4(cur, s_cur, l, s_r);
-            np[1] = make_int4(__float_as_int(bx), __float_as_int(tx), __float_as_int(by), __float_as_int(ty));
-            np[2] = make_int4(__float_as_int(sbx), __float_as_int(stx), __float_as_int(sby), __float_as_int(sty));
-            np[3] = make_int4(__float_as_int(bz), __float_as_int(tz), __float_as_int(sbz), __float_as_int(stz));
-            cur = parent; r = s_r;
-            bx = fminf(bx, sbx); by = fminf(by, sby); bz = fminf(bz, sbz);
-            tx = fmaxf(tx, stx); ty = fmaxf(ty, sty); tz = fmaxf(tz, stz);
+    // ---- (2a) the warp's 32 leaves ----
+    S.l = S.r = leaf;
+    S.cur = leaf + n_nodes;            // child index >= n_nodes marks a leaf
+    S.dl = ld_shifted[min(leaf, L)];            // delta(leaf - 1)
+    S.dr = ld_shifted[min(leaf + 1, L)];        // delta(leaf)
+    nd_merge_rounds<T>(S, active, lane, nodes);
+
+    // ---- (2b) what the block's warps have left, in order, through shared memory ----
+    const unsigned amask = __ballot_sync(0xffffffffu, active);
+    if (lane == 0) s_cnt[warp] = __popc(amask);
+    __syncthreads();
+    int base = 0, m = 0;
+#pragma unroll
+    for (int k = 0; k < ND_WARPS; ++k) { if (k < warp) base += s_cnt[k]; m += s_cnt[k]; }
+    if (active) s_sub[base + __popc(amask & ((1u << lane) - 1u))] = S;
+    __syncthreads();
+    if (warp == 0) {
+        // sweeps over windows of 32 subtrees; survivors are compacted to the front.  A pair
+        // straddling a window boundary may stay unmerged: stage (3) takes whatever is left.
+        int count = m;
+        for (int sweep = 0; sweep < 4 && count > 1; ++sweep) {
+            int out = 0;
+            bool merged_any = false;
+            for (int wb = 0; wb < count; wb += 32) {
+                bool act = wb + lane < count;
+                NdSub<T> X = s_sub[min(wb + lane, ND_THREADS - 1)];
+                const int before = __popc(__ballot_sync(0xffffffffu, act));
+                nd_merge_rounds<T>(X, act, lane, nodes);
+                const unsigned am = __ballot_sync(0xffffffffu, act);
+                merged_any |= __popc(am) != before;
+                __syncwarp();
+                if (act) s_sub[out + __popc(am & ((1u << lane) - 1u))] = X;     // out <= wb: never ahead of the reads
+                out += __popc(am);
+                __syncwarp();
+            }
+            count = out;
+            if (!merged_any) break;
         }
-        if ((absorbed >> lane) & 1u) active = false;
+        if (lane == 0) s_m = count;
     }
-    // ---- (3) climb across warps ----
+    __syncthreads();
+    m = s_m;
+
+    // ---- (3) climb across blocks ----
+    active = (int)threadIdx.x < m;
+    if (active) S = s_sub[threadIdx.x];
+    int cur = S.cur, l = S.l, r = S.r;
+    float bx = S.bx, by = S.by, bz = S.bz, tx = S.tx, ty = S.ty, tz = S.tz;
+    bool right_child = active && S.dl < S.dr;
+    int parent = right_child ? l - 1 : r;
     while (active) {
         // parent / right_child are current for [l, r] on entry
         if (parent < 0 || parent >= n_nodes) { *root = cur; break; }
@@ -408,6 +467,7 @@ nodes_kernel(const float4* __restrict__ spheres, const int4* __restrict__ leaves
         right_child = dl < dr;
         parent = right_child ? l - 1 : r;
     }
+    __syncthreads();       // s_sub is reused by the next window
     }
 }
 
