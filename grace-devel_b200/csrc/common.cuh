@@ -19,7 +19,7 @@ struct grace_b200_ctx {
     int* h_pinned = nullptr;   // pinned host mirror for count read-backs
     int last_n_leaves_valid = 0;
     int trace_mode = GRACE_B200_TRACE_PACKET;
-    int trace_budget = 2048;   // traversal steps before a packet may be split (0 = never)
+    int trace_budget = 1024;   // traversal steps before a packet may be split (0 = never)
     int trace_dynamic = 0;     // 1: suspended traversals are resumed inside the same launch
     int trace_resume_per_ray = 0;   // 1: suspended packets continue one ray per lane (second launch)
     // file-loader staging (gadget_io.cu): two pinned host buffers + completion events, kept

@@ -899,7 +899,11 @@ trace_packet_kernel(const PkArgs P, const PkTasks T)
                 __syncwarp();
                 if (PROF) { ++pf_leaves; pf_staged += cnt; pf_kept += n_kept; }
                 const int k_active = __popc(leaf_mask);
-                if (3 * k_active < 2 * n_kept) {
+#ifndef PK_SPARSE_NUM
+#define PK_SPARSE_NUM 3
+#define PK_SPARSE_DEN 2
+#endif
+                if (PK_SPARSE_NUM * k_active < PK_SPARSE_DEN * n_kept) {
                     if (common) pk_leaf_sparse<MODE, M4, true>(W, leaf_mask, n_kept, lane, lt, A, s_table);
                     else pk_leaf_sparse<MODE, M4, false>(W, leaf_mask, n_kept, lane, lt, A, s_table);
                 } else {

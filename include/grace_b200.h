@@ -179,7 +179,7 @@ int grace_b200_set_trace_mode(grace_b200_ctx* ctx, int mode);
  * packet still running after `steps` inner-node + leaf visits is suspended and resumed as
  * several tasks over disjoint subsets of its rays, so the tail of heavy packets spreads over the
  * idle SMs (results are unaffected: each ray accumulates in the same order).  0 disables
- * splitting; the default is 2048.  OR-ing GRACE_B200_BUDGET_EAGER into `steps` suspends every
+ * splitting; the default is 1024.  OR-ing GRACE_B200_BUDGET_EAGER into `steps` suspends every
  * packet at `steps` whether or not unclaimed work is left (used by the tests to force splits). */
 #define GRACE_B200_BUDGET_EAGER (1 << 30)
 int grace_b200_set_trace_budget(grace_b200_ctx* ctx, int steps);

@@ -20,7 +20,7 @@ for mode in ("packet", "packet_wide", "ray", "packet_ref"):
         idx, integ, dist = gb.trace_sph(rays, d, tree, off)
         gb.sort_by_distance(dist, off, idx, integ)
         tau = torch.empty_like(integ); gb.exclusive_segmented_scan(off, integ, tau)
-gb.set_trace_mode("packet"); gb.set_trace_budget(2048); gb.set_trace_dynamic(0); gb.set_trace_resume(0)
+gb.set_trace_mode("packet"); gb.set_trace_budget(1024); gb.set_trace_dynamic(0); gb.set_trace_resume(0)
 r2 = torch.empty((4096, 7), dtype=torch.float32, device="cuda")
 gb.uniform_random_rays(r2, 0.5, 0.5, 0.5, 2.0, 7)
 gb.orthographic_projection_rays(None, 64, 32, (0.5, 0.5, 2.0), (0.5, 0.5, 0.5), (0, 1, 0), 1.0, 3.0)

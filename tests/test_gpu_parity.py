@@ -297,7 +297,7 @@ def test_packet_splitting_is_exact(gb, orc, scene, budget, dynamic, trace_mode):
         assert np.array_equal(host(integ).view(np.uint32), rinteg.view(np.uint32))
         assert np.array_equal(host(dist).view(np.uint32), rdist.view(np.uint32))
     finally:
-        gb.set_trace_budget(2048)
+        gb.set_trace_budget(1024)
         gb.set_trace_dynamic(False)
         gb.set_trace_resume(False)
 
