@@ -583,8 +583,7 @@ int launch_packet(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, int n_packe
         T.budget = ctx->trace_budget & 0x3fffffff;
         T.eager = (ctx->trace_budget & GRACE_B200_BUDGET_EAGER) ? 1 : 0;
         T.tasks_out = lists[0]; T.n_tasks_out = n_counts + 1; T.child_width = 32;
-        const bool crowded = (size_t)n_packets * 2 >= (size_t)full_grid * PK_WARPS;
-        T.sum_steps = (unsigned long long*)(n_counts + 4); T.n_done = crowded ? n_counts + 6 : nullptr;
+        T.sum_steps = (unsigned long long*)(n_counts + 4); T.n_done = n_counts + 6;
         GB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
         kernel<<<blocks, PK_THREADS, psmem, st>>>(P, T);
         GB_LAUNCH_CHECK();
@@ -603,9 +602,10 @@ int launch_packet(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, int n_packe
             T.records = records; T.n_records = n_counts; T.records_cap = records_cap; T.tasks_cap = tasks_cap;
             T.budget = ctx->trace_budget & 0x3fffffff;
             T.eager = (ctx->trace_budget & GRACE_B200_BUDGET_EAGER) ? 1 : 0;
-            // fewer packets than warps: idle capacity exists from the start, split on the budget alone
-            const bool crowded = round > 0 || (size_t)n_packets * 2 >= (size_t)full_grid * PK_WARPS;
-            T.sum_steps = (unsigned long long*)(n_counts + 4); T.n_done = crowded ? n_counts + 6 : nullptr;
+            // Round 0 whose children (32/8 per packet) would all fit on idle warps: split on the
+            // budget alone.  Otherwise a unit must also be heavier than the launch's running mean.
+            const bool roomy = round == 0 && (size_t)n_packets * (32 / widths[0]) <= (size_t)full_grid * PK_WARPS;
+            T.sum_steps = (unsigned long long*)(n_counts + 4); T.n_done = roomy ? nullptr : n_counts + 6;
             if (round > 0) GB_CUDA(cudaMemsetAsync(n_counts + 4, 0, 3 * sizeof(int), st));        // per-round statistics
             if (round > 0) { T.tasks_in = lists[(round - 1) & 1]; T.n_tasks_in = n_counts + 1 + ((round - 1) & 1); }
             if (round < n_rounds - 1) {

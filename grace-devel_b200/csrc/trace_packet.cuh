@@ -658,6 +658,7 @@ trace_packet_kernel(const PkArgs P, const PkTasks T)
                     const long long nd = *(volatile int*)T.n_done;
                     const unsigned long long ss = *(volatile unsigned long long*)T.sum_steps;
                     if (nd > 0) split_now = 4ll * (guard0 - guard) * nd >= (long long)PK_AVG_FACTOR_X4 * (long long)ss;
+                    else split_now = guard0 - guard >= 8 * T.budget;      // nothing to compare with yet
                 }
             }
             if (split_now) {
