@@ -15,129 +15,151 @@
 
 namespace grace {
 
-class Init_null {
-public:
-    __device__ void operator()(const gpu::BoundIter<char>) {}
+namespace detail {
+
+typedef gpu::BoundIter<char> SmemBlock;   // the user's shared-memory block as every functor receives it
+
+// One hit's contribution to a column density: the kernel line integral at impact parameter
+// sqrt(b2), for a particle of smoothing length h.  The table (n_table doubles) is read through
+// the bounds-checked iterator.  Operation order is the reference's (cuda/functors/trace.cuh:183-191
+// and :221-228): 1/h, then (n-1)*(sqrt(b2)/h) as written, lerp, then times (1/h)^2.
+template <typename Real, typename Real4>
+__device__ __forceinline__ Real sph_line_integral(const Real4& sphere, const Real b2, const SmemBlock smem, const int n_table)
+{
+    const gpu::BoundIter<double> table = smem;
+    const Real inv_h = 1.f / sphere.w;
+    const Real pos = (n_table - 1) * (sqrt(b2) * inv_h);
+    Real w = lerp(pos, table, n_table);
+    w *= (inv_h * inv_h);
+    return w;
+}
+
+} // namespace detail
+
+// ---- no-ops -------------------------------------------------------------------------------
+
+struct Init_null {
+    __device__ void operator()(detail::SmemBlock) {}
 };
 
-class RayEntry_null {
-public:
+struct RayEntry_null {
     template <typename RayData>
-    __device__ void operator()(const int, const Ray&, const RayData&, const gpu::BoundIter<char>) {}
+    __device__ void operator()(int, const Ray&, const RayData&, detail::SmemBlock) {}
 };
 typedef RayEntry_null RayExit_null;
 
+// ---- per-ray state in / out of global arrays ----------------------------------------------
+
 template <typename T>
-class RayEntry_from_array {
-    const T* const inits;
-public:
-    RayEntry_from_array(const T* const ray_data_inits) : inits(ray_data_inits) {}
+struct RayEntry_from_array {
+    RayEntry_from_array(const T* per_ray_initial) : src_(per_ray_initial) {}
+
     template <typename RayData>
-    __device__ void operator()(const int ray_idx, const Ray&, RayData& ray_data, const gpu::BoundIter<char>)
-    {
-        ray_data.data = inits[ray_idx];
-    }
+    __device__ void operator()(int ray, const Ray&, RayData& state, detail::SmemBlock) { state.data = src_[ray]; }
+
+private:
+    const T* src_;
 };
 
 template <typename T>
-class RayExit_to_array {
-    T* const store;
-public:
-    RayExit_to_array(T* const ray_data_store) : store(ray_data_store) {}
+struct RayExit_to_array {
+    RayExit_to_array(T* per_ray_result) : dst_(per_ray_result) {}
+
     template <typename RayData>
-    __device__ void operator()(const int ray_idx, const Ray&, const RayData& ray_data, const gpu::BoundIter<char>)
-    {
-        store[ray_idx] = ray_data.data;
-    }
+    __device__ void operator()(int ray, const Ray&, const RayData& state, detail::SmemBlock) { dst_[ray] = state.data; }
+
+private:
+    T* dst_;
 };
 
-// Copies `count` values from global to the user's shared-memory block (the kernel synchronises after).
+// ---- block set-up --------------------------------------------------------------------------
+
+// Stages `n` values of T from global memory at the start of the user's shared-memory block;
+// the traversal kernel synchronises the block after Init returns.
 template <typename T>
-class InitGlobalToSmem {
-    const T* const data_global;
-    const int count;
-public:
-    InitGlobalToSmem(const T* const global_addr, const int count) : data_global(global_addr), count(count) {}
-    __device__ void operator()(const gpu::BoundIter<char> smem_iter)
+struct InitGlobalToSmem {
+    InitGlobalToSmem(const T* global_values, int n) : src_(global_values), n_(n) {}
+
+    __device__ void operator()(detail::SmemBlock smem)
     {
-        gpu::BoundIter<T> T_iter = smem_iter;
-        for (int i = threadIdx.x; i < count; i += blockDim.x) T_iter[i] = data_global[i];
+        gpu::BoundIter<T> dst = smem;
+        for (int k = threadIdx.x; k < n_; k += blockDim.x) dst[k] = src_[k];
     }
+
+private:
+    const T* src_;
+    int n_;
 };
 
-class Intersect_sphere_bool {
-public:
+// ---- ray/sphere intersection ---------------------------------------------------------------
+
+struct Intersect_sphere_bool {
     template <typename Real4, typename RayData>
-    __device__ bool operator()(const Ray& ray, const Real4& sphere, const RayData&, const int, const gpu::BoundIter<char>)
+    __device__ bool operator()(const Ray& ray, const Real4& sphere, const RayData&, int, detail::SmemBlock)
     {
-        typedef typename Real4ToRealMapper<Real4>::type Real;
-        Real b2, dist;
-        return sphere_hit(ray, sphere, b2, dist);
+        typename Real4ToRealMapper<Real4>::type unused_b2, unused_dist;
+        return sphere_hit(ray, sphere, unused_b2, unused_dist);
     }
 };
 
-class Intersect_sphere_b2dist {
-public:
+// Leaves the squared impact parameter and the distance to the point of closest approach in the
+// ray's state for the OnHit functors below.
+struct Intersect_sphere_b2dist {
     template <typename Real4, typename RayData>
-    __device__ bool operator()(const Ray& ray, const Real4& sphere, RayData& ray_data, const int, const gpu::BoundIter<char>)
+    __device__ bool operator()(const Ray& ray, const Real4& sphere, RayData& state, int, detail::SmemBlock)
     {
-        return sphere_hit(ray, sphere, ray_data.b2, ray_data.dist);
+        return sphere_hit(ray, sphere, state.b2, state.dist);
     }
 };
 
-class OnHit_increment {
-public:
+// ---- on hit --------------------------------------------------------------------------------
+
+struct OnHit_increment {
     template <typename RayData, typename TPrim>
-    __device__ void operator()(const int, const Ray&, RayData& ray_data, const int, const TPrim&, const int,
-                               const gpu::BoundIter<char>)
+    __device__ void operator()(int, const Ray&, RayData& state, int, const TPrim&, int, detail::SmemBlock)
     {
-        ++ray_data.data;
+        ++state.data;
     }
 };
 
-// Accumulates kernel line integrals; the double-precision table sits at the start of the user's
-// shared-memory block (InitGlobalToSmem<double>).
-class OnHit_sphere_cumulate {
-    const int N_table;
-public:
-    OnHit_sphere_cumulate(const int N_table) : N_table(N_table) {}
+// Column density: state.data += line integral.  Expects the double-precision table at the start
+// of the shared-memory block (InitGlobalToSmem<double>).
+struct OnHit_sphere_cumulate {
+    OnHit_sphere_cumulate(int n_table) : n_table_(n_table) {}
+
     template <typename RayData, typename Real4>
-    __device__ void operator()(const int, const Ray&, RayData& ray_data, const int, const Real4& sphere, const int,
-                               const gpu::BoundIter<char> smem_iter)
+    __device__ void operator()(int, const Ray&, RayData& state, int, const Real4& sphere, int, detail::SmemBlock smem)
     {
         typedef typename Real4ToRealMapper<Real4>::type Real;
-        gpu::BoundIter<double> Wk_lookup = smem_iter;
-        Real ir = 1.f / sphere.w;
-        Real b = (N_table - 1) * (sqrt(ray_data.b2) * ir);
-        Real integral = lerp(b, Wk_lookup, N_table);
-        integral *= (ir * ir);
-        ray_data.data += integral;
+        state.data += detail::sph_line_integral<Real>(sphere, state.b2, smem, n_table_);
     }
+
+private:
+    int n_table_;
 };
 
+// Hit lists: state.data is the ray's write cursor (initialised to its offset by
+// RayEntry_from_array), one (index, integral, distance) record per hit.
 template <typename IndexType, typename Real>
-class OnHit_sphere_individual {
-    IndexType* const indices;
-    Real* const integrals;
-    Real* const distances;
-    const int N_table;
-public:
-    OnHit_sphere_individual(IndexType* const indices, Real* const integrals, Real* const distances, const int N_table)
-        : indices(indices), integrals(integrals), distances(distances), N_table(N_table) {}
+struct OnHit_sphere_individual {
+    OnHit_sphere_individual(IndexType* hit_indices, Real* hit_integrals, Real* hit_distances, int n_table)
+        : idx_(hit_indices), w_(hit_integrals), dist_(hit_distances), n_table_(n_table) {}
+
     template <typename RayData, typename Real4>
-    __device__ void operator()(const int, const Ray&, RayData& ray_data, const int sphere_idx, const Real4& sphere,
-                               const int, const gpu::BoundIter<char> smem_iter)
+    __device__ void operator()(int, const Ray&, RayData& state, int prim, const Real4& sphere, int, detail::SmemBlock smem)
     {
-        gpu::BoundIter<double> Wk_lookup = smem_iter;
-        Real ir = 1.f / sphere.w;
-        Real b = (N_table - 1) * (sqrt(ray_data.b2) * ir);
-        Real integral = lerp(b, Wk_lookup, N_table);
-        integral *= (ir * ir);
-        indices[ray_data.data] = sphere_idx;
-        integrals[ray_data.data] = integral;
-        distances[ray_data.data] = ray_data.dist;
-        ++ray_data.data;
+        const Real w = detail::sph_line_integral<Real>(sphere, state.b2, smem, n_table_);
+        const int slot = state.data++;
+        idx_[slot] = prim;
+        w_[slot] = w;
+        dist_[slot] = state.dist;
     }
+
+private:
+    IndexType* idx_;
+    Real* w_;
+    Real* dist_;
+    int n_table_;
 };
 
 } // namespace grace

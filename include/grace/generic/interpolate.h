@@ -1,6 +1,9 @@
-// grace/generic/interpolate.h -- linear table interpolation (reference:
-// generic/interpolate.h:11-39).  x in [0, N_table); the result is evaluated in the table's
-// precision, as y0 + t*(y1 - y0) (adjacent entries: the difference is exact by Sterbenz).
+// grace/generic/interpolate.h -- piecewise-linear lookup in an evenly spaced table (reference
+// behaviour: generic/interpolate.h:11-39).  `x` is the position in units of the table spacing,
+// 0 <= x; positions at or beyond the last entry return the last entry.  The arithmetic runs in
+// the TABLE's precision (double for the SPH kernel integrals), whatever Real is:
+// y[c] + (x - c) * (y[c+1] - y[c]), fused on the device; adjacent entries are close enough for
+// the difference to be exact.
 #pragma once
 #include <iterator>
 #include "grace/types.h"
@@ -10,15 +13,21 @@ namespace grace {
 template <typename Real, typename TableIter>
 GRACE_HOST_DEVICE Real lerp(Real x, TableIter table, int N_table)
 {
-    typedef typename std::iterator_traits<TableIter>::value_type TableReal;
-    int i = static_cast<int>(x);
-    if (i >= N_table - 1) { x = static_cast<TableReal>(N_table - 1); i = N_table - 2; }
-    const TableReal y0 = table[i], y1 = table[i + 1];
-    const TableReal t = static_cast<TableReal>(x) - i;
+    typedef typename std::iterator_traits<TableIter>::value_type Y;
+    const int last = N_table - 1;
+    int cell = static_cast<int>(x);
+    Y pos = static_cast<Y>(x);
+    if (cell >= last) {               // clamp to the right edge of the last cell
+        cell = last - 1;
+        pos = static_cast<Y>(last);
+    }
+    const Y left = table[cell];
+    const Y rise = table[cell + 1] - left;
+    const Y frac = pos - cell;
 #ifdef __CUDA_ARCH__
-    return fma(t, y1 - y0, y0);
+    return fma(frac, rise, left);
 #else
-    return t * (y1 - y0) + y0;
+    return frac * rise + left;
 #endif
 }
 

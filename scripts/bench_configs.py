@@ -176,4 +176,11 @@ if 5 in want:
     out["config5_one_to_many_healpix"] = dict(n=n5, rays=r5, nside=2048, build_ms_incl_first_call=build_ms, n_leaves=tree5.n_leaves,
         gen_rays_ms=t_gen, cumulative_ms=t_cum, mrays_s=r5 / t_cum / 1e3, device_error=gb.device_error(),
         mean_column_density=float(cum.double().mean().item()))
+    # run (B) of SURVEY 8d: the full sky at nside = 1024 (12 * 1024^2 = 12 582 912 rays, a multiple of 32)
+    rb = 12 * 1024 * 1024
+    t_gen_b = timed(lambda: gb.healpix_rays(rays[:rb], 1024, 0, rb, c, c, c, length), reps=2)
+    t_cum_b = timed(lambda: gb.trace_cumulative_sph(rays[:rb], s5, tree5, cum[:rb]), reps=2)
+    out["config5b_full_sky_healpix"] = dict(n=n5, rays=rb, nside=1024, gen_rays_ms=t_gen_b, cumulative_ms=t_cum_b,
+        mrays_s=rb / t_cum_b / 1e3, device_error=gb.device_error(),
+        mean_column_density=float(cum[:rb].double().mean().item()))
 print(json.dumps(out))
