@@ -327,6 +327,10 @@ __device__ __forceinline__ bool pk_test(const float4 s, float ox, float oy, floa
 // lane's FIFO; the loop body has no vote and no branch: it runs for `room` spheres, the
 // number of pushes every lane's FIFO is known to have space for, and only then looks at the
 // fill levels again.
+#ifndef PK_SPARSE_NUM
+#define PK_SPARSE_NUM 3
+#define PK_SPARSE_DEN 2
+#endif
 #ifndef PK_PAIRS_OK
 #define PK_PAIRS_OK(mode) ((mode) == MODE_CUMULATIVE)      // hit lists carry twice the per-hit state: no gain there
 #endif
@@ -640,7 +644,8 @@ trace_packet_kernel(const PkArgs P, const PkTasks T)
         }
         __syncwarp();
 
-        unsigned long long pf_nodes = 0, pf_leaves = 0, pf_staged = 0, pf_kept = 0;
+        unsigned long long pf_nodes = 0, pf_leaves = 0, pf_staged = 0, pf_kept = 0, pf_l1 = 0, pf_l2 = 0, pf_l3 = 0;
+        (void)pf_l1; (void)pf_l2; (void)pf_l3;
         const long long pf_t0 = PROF ? clock64() : 0;
         const int guard0 = 2 * n_nodes + 8;   // a depth-first walk enters each node at most once
         int guard = guard0;
@@ -900,9 +905,11 @@ trace_packet_kernel(const PkArgs P, const PkTasks T)
                 __syncwarp();
                 if (PROF) { ++pf_leaves; pf_staged += cnt; pf_kept += n_kept; }
                 const int k_active = __popc(leaf_mask);
-#ifndef PK_SPARSE_NUM
-#define PK_SPARSE_NUM 3
-#define PK_SPARSE_DEN 2
+#ifdef PK_PROF_LANES      // diagnostic build: lane efficiency of the leaf tests instead of the usual per-packet record
+                if (PROF) {
+                    if (PK_SPARSE_NUM * k_active < PK_SPARSE_DEN * n_kept) pf_l3 += (unsigned long long)n_kept * k_active;
+                    else { pf_l1 += (unsigned long long)n_kept * k_active; pf_l2 += n_kept; }
+                }
 #endif
                 if (PK_SPARSE_NUM * k_active < PK_SPARSE_DEN * n_kept) {
                     if (common) pk_leaf_sparse<MODE, M4, true>(W, leaf_mask, n_kept, lane, lt, A, s_table);
@@ -925,6 +932,9 @@ trace_packet_kernel(const PkArgs P, const PkTasks T)
             atomicAdd(P.prof + 2, pf_staged); atomicAdd(P.prof + 3, pf_kept);
             unsigned long long* pp = P.prof + 4 + 4 * (size_t)packet;   // per-packet record
             pp[0] = (unsigned long long)(clock64() - pf_t0); pp[1] = pf_nodes; pp[2] = pf_leaves; pp[3] = pf_kept;
+#ifdef PK_PROF_LANES
+            pp[1] = pf_l1; pp[2] = pf_l2; pp[3] = pf_l3;
+#endif
         }
     }
 }
