@@ -503,8 +503,14 @@ struct PkArgs {
         }                                                                                \
     } while (0)
 
+// Hit counts carry no FIFO and no accumulators: 72 registers cost them nothing and the seventh CTA
+// per SM is worth 4 % (13.4 -> 12.8 ms); with the column-density state 72 registers spill and the
+// gain is within noise (orthographic tiles lose 5 %), so those modes stay at 6 CTAs.
+#ifndef PK_MIN_BLOCKS_COUNT_V
+#define PK_MIN_BLOCKS_COUNT_V 7
+#endif
 template <int MODE, int M4, bool PROF, bool WIDE>
-__global__ void __launch_bounds__(PK_THREADS, PK_MIN_BLOCKS)
+__global__ void __launch_bounds__(PK_THREADS, (MODE == MODE_COUNT && !PROF && !WIDE) ? PK_MIN_BLOCKS_COUNT_V : PK_MIN_BLOCKS)
 trace_packet_kernel(const PkArgs P, const PkTasks T)
 {
     using Warp = PkWarp<MODE, M4>;

@@ -14,7 +14,7 @@ tile = 1 << 16
 subs = [rays[(k * (side * side // 8)) // 32 * 32:][:tile].contiguous() for k in range(8)]
 off = torch.empty(tile, dtype=torch.int32, device="cuda")
 cum = torch.empty(tile, dtype=torch.float32, device="cuda")
-for b in (512, 1024, 2048, 4096):
+for b in [int(x) for x in os.environ.get("AB_BUDGETS", "512,1024,2048,4096").split(",")]:
     gb.set_trace_budget(b)
     t_l = t_c = 0.0
     for sub in subs:
