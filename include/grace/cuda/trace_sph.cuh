@@ -27,6 +27,26 @@ struct KernelIntegrals {
 
 namespace detail {
 inline const grace_b200_ray* rays_ptr(const Ray* r) { return reinterpret_cast<const grace_b200_ray*>(r); }
+
+// GRACE_DEBUG builds of the reference assert inside the kernel when a traversal stack overflows
+// (bintree_trace.cuh:162-164) and synchronise after every launch (error.h:57-64).  The B200
+// kernels raise a device-side flag instead (1 = stack overflow, 2 = walk did not terminate: a
+// malformed tree); with GRACE_DEBUG defined it is read back after every trace -- one stream
+// synchronisation, as in the reference's debug builds -- and reported the way error.h reports.
+inline void debug_check_trace(const char* what)
+{
+#ifdef GRACE_DEBUG
+    int flag = 0;
+    GRACE_B200_CHECK(grace_b200_device_error(context(), &flag, nullptr));
+    if (flag != 0) {
+        std::fprintf(stderr, "**** GRACE device-side error %d in %s (%s)\n", flag, what,
+                     flag == 1 ? "traversal stack overflow" : "traversal did not terminate");
+        std::exit(EXIT_FAILURE);
+    }
+#else
+    (void)what;
+#endif
+}
 }
 
 // All throw std::invalid_argument unless d_rays.size() % 32 == 0.
@@ -39,6 +59,7 @@ GRACE_HOST void trace_hitcounts_sph(const RayVec& d_rays, const SphereVec& d_sph
         detail::context(), detail::rays_ptr(detail::raw(d_rays.data())), d_rays.size(),
         reinterpret_cast<const float*>(detail::raw(d_spheres.data())), d_spheres.size(), &t,
         detail::raw(d_hit_counts.data()), nullptr));
+    detail::debug_check_trace("trace_hitcounts_sph");
 }
 
 template <typename RayVec, typename SphereVec, typename RealVec, detail::if_elem<SphereVec, float4> = 0>
@@ -50,6 +71,7 @@ GRACE_HOST void trace_cumulative_sph(const RayVec& d_rays, const SphereVec& d_sp
         detail::context(), detail::rays_ptr(detail::raw(d_rays.data())), d_rays.size(),
         reinterpret_cast<const float*>(detail::raw(d_spheres.data())), d_spheres.size(), &t,
         detail::raw(d_cumulated.data()), nullptr));
+    detail::debug_check_trace("trace_cumulative_sph");
 }
 
 namespace detail {
@@ -78,6 +100,7 @@ inline void trace_lists(const RayVec& d_rays, const SphereVec& d_spheres, const 
                                                        raw(d_ray_offsets.data()), raw(d_hit_indices.data()),
                                                        raw(d_hit_integrals.data()), raw(d_hit_distances.data()),
                                                        nullptr));
+    debug_check_trace("trace_sph");
 }
 } // namespace detail
 
