@@ -321,6 +321,10 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_val = world * r / (float(e2e_ms.item()) / args.steps * 1e-3) / 1e6
+    # a number from a traversal that overflowed its stack or did not terminate is not a number
+    derr = gb.device_error()
+    if derr != 0:
+        raise SystemExit(f"bench: device-side trace error {derr} on rank {rank}")
 
     if rank != 0:
         if world > 1:
