@@ -37,7 +37,7 @@ enum {
     GB_SC_ERRFLAG = 5,      // device-side error flag (trace stack overflow)
     GB_SC_TOTAL64 = 8,      // 64-bit total (2 ints), 8-byte aligned
     GB_SC_TASKS = 32,       // trace load balancing: record count + two task-list counts
-    GB_SC_CLASS = 16,       // segmented sort class counters (8 ints) + XL total (2 ints)
+    GB_SC_CLASS = 40,       // segmented sort class counters (16 ints) + XL total (2 ints, 8-byte aligned)
     GB_SC_COUNT = 64
 };
 
