@@ -378,7 +378,8 @@ def test_hit_lists_with_sentinels(gb, orc, scene):
 
 def test_segsort_all_classes(gb, orc):
     # segment lengths straddling every size class incl. the global-memory path
-    lens = [0, 1, 2, 31, 32, 33, 500, 512, 513, 2048, 2049, 8192, 8193, 20000, 3, 0, 40000]
+    lens = [0, 1, 2, 31, 32, 33, 500, 512, 513, 1023, 1024, 1025, 1536, 1537, 2048, 2049, 3072, 3073,
+            4096, 4097, 6144, 6145, 8192, 8193, 20000, 3, 0, 40000]
     rng = np.random.default_rng(3)
     total = sum(lens)
     dist = rng.integers(0, 1000, total).astype(np.float32) / np.float32(7.0)   # many ties
