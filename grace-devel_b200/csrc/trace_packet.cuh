@@ -148,20 +148,45 @@ __device__ __noinline__ float pk_flush_cum(PkWarp<MODE, M4>& W, int qn, float cu
     return cum;
 }
 
+// Hit lists: evaluate and store in one go.  The occupied cells are listed RAY-major (a shuffle
+// scan of the fill levels gives every lane the start of its run), so the 32 cells a step
+// handles belong to a few rays and land on a few contiguous stretches of each output array:
+// ~6 sectors per store instruction where one lane per ray wrote 32 (the fill pass was bound by
+// those scattered 4-byte stores).  Values and positions are exactly those of the per-lane loop.
 template <int MODE, int M4>
 __device__ __noinline__ int pk_flush_fill(PkWarp<MODE, M4>& W, int qn, int cursor, int lane, unsigned lt, const double2* table,
                                           int* hit_idx, float* hit_integral, float* hit_dist)
 {
-    pk_flush_eval<MODE, M4>(W, qn, lane, lt, table);
-    for (int j = 0; j < qn; ++j) {
-        const float2 e2 = W.q2[j * 32 + lane];
-        hit_idx[cursor] = __float_as_int(e2.y);
-        hit_integral[cursor] = W.q[j * 32 + lane].x;
-        hit_dist[cursor] = e2.x;
-        ++cursor;
+    (void)lt;
+    __syncwarp();       // entries may have been written by other lanes (transposed leaves)
+    int incl = qn;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int first = incl - qn;
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll
+    for (int j = 0; j < PK_QD; ++j)
+        if (j < qn) W.cells[first + j] = (unsigned char)(j * 32 + lane);
+    __syncwarp();
+    for (int base = 0; base < total; base += 32) {
+        const int k = base + lane;
+        const bool on = k < total;
+        const int c = on ? W.cells[k] : 0;
+        const int cur = __shfl_sync(0xffffffffu, cursor, c & 31);     // the owning ray's write position
+        if (on) {
+            const float2 e = W.q[c], e2 = W.q2[c];
+            const float w = pk_lerp(e.x, e.y, table);
+            const int pos = cur + (c >> 5);
+            hit_idx[pos] = __float_as_int(e2.y);
+            hit_integral[pos] = __fmul_rn(w, __fmul_rn(e.y, e.y));     // OnHit_sphere_individual: one FMUL
+            hit_dist[pos] = e2.x;
+        }
     }
     __syncwarp();
-    return cursor;
+    return cursor + qn;
 }
 
 template <int MODE, int M4>
