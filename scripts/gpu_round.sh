@@ -6,6 +6,7 @@ TAG=${1:-r1b}
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest rc=$?"
 tail -3 gpurun_out/pytest_$TAG.log
 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"
+[ -n "${SKIP_NCU:-}" ] && exit 0     # measurements only: the profiled kernels did not change
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-reference-cuda"
 $CMD > gpurun_out/plain_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_l_$TAG.log 2>&1

@@ -4,6 +4,7 @@
 set -e
 TAG=${1:?tag}; R=${2:-r1}
 cd "$(dirname "$0")/.."
+if [ -f gpurun_out/trace_$TAG.ncu-rep ]; then
 python scripts/ncu_summary.py gpurun_out/trace_$TAG.ncu-rep > profiles/${R}_trace_packet_ncu_full.json
 python scripts/ncu_summary.py gpurun_out/build_$TAG.ncu-rep > profiles/${R}_build_kernels_ncu_full.json
 ncu -i gpurun_out/trace_$TAG.ncu-rep --page source --print-source cuda,sass --csv > /tmp/trace_src_$TAG.csv 2>/dev/null
@@ -21,8 +22,9 @@ json.dump({"dram_bytes_per_launch": r + w, "dram_bytes_read": r, "dram_bytes_wri
            "what": f"sum of dram__bytes_read.sum + dram__bytes_write.sum over the {len(d)} launches of trace_packet_kernel<cumulative,32> in one trace_cumulative_sph call (2^24 particles, 2^20 rays), ncu --set full, profiles/{R}_trace_packet_ncu_full.json"},
           open("profiles/trace_traffic.json", "w"), indent=1)
 PY
-cp gpurun_out/bench_$TAG.json profiles/${R}_bench_n1.json
 cp gpurun_out/launches_$TAG.csv profiles/${R}_launches.csv
+fi      # (a SKIP_NCU=1 round leaves the ncu summaries of the previous round in place)
+cp gpurun_out/bench_$TAG.json profiles/${R}_bench_n1.json
 cp gpurun_out/compare_reference_cuda_2p24_2p20.json profiles/${R}_compare_reference_cuda_2p24_2p20.json
 tail -1 gpurun_out/compare_lists_$TAG.log | python -m json.tool > profiles/${R}_compare_lists_2p24_2p17.json
 python - "$TAG" "$R" <<'PY'
