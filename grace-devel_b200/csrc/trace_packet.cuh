@@ -40,7 +40,7 @@ constexpr int PK_WARPS = PK_THREADS / 32;
 #endif
 constexpr int PK_MIN_BLOCKS = PK_MIN_BLOCKS_V;   // register budget: 65536 / (6 * 128) = 85
 #ifndef PK_STACK_V
-#define PK_STACK_V 256
+#define PK_STACK_V 192
 #endif
 constexpr int PK_STACK = PK_STACK_V;  // reference STACK_SIZE is 64 (kernel_config.h:13)
 #ifndef PK_DFS_RESERVE_V
@@ -528,14 +528,16 @@ struct PkArgs {
         }                                                                                \
     } while (0)
 
-// Hit counts carry no FIFO and no accumulators: 72 registers cost them nothing and the seventh CTA
-// per SM is worth 4 % (13.4 -> 12.8 ms); with the column-density state 72 registers spill and the
-// gain is within noise (orthographic tiles lose 5 %), so those modes stay at 6 CTAs.
-#ifndef PK_MIN_BLOCKS_COUNT_V
-#define PK_MIN_BLOCKS_COUNT_V 7
+// Seven CTAs per SM (72 registers) for hit counts and column densities: hit counts carry no FIFO
+// and no accumulators and gain 4 % (13.4 -> 12.8 ms); the column-density kernel spills 48 bytes at
+// 72 registers and still gains 1.3 % at 2^20 rays and 4.5 % at 2^17 (the 192-entry stack is what
+// lets the seventh CTA's shared memory fit).  Hit lists (more shared memory) stay at 6.
+#ifndef PK_MIN_BLOCKS_LIGHT_V
+#define PK_MIN_BLOCKS_LIGHT_V 7
 #endif
 template <int MODE, int M4, bool PROF, bool WIDE>
-__global__ void __launch_bounds__(PK_THREADS, (MODE == MODE_COUNT && !PROF && !WIDE) ? PK_MIN_BLOCKS_COUNT_V : PK_MIN_BLOCKS)
+__global__ void __launch_bounds__(PK_THREADS, ((MODE == MODE_COUNT || MODE == MODE_CUMULATIVE) && !PROF && !WIDE)
+                                                  ? PK_MIN_BLOCKS_LIGHT_V : PK_MIN_BLOCKS)
 trace_packet_kernel(const PkArgs P, const PkTasks T)
 {
     using Warp = PkWarp<MODE, M4>;
