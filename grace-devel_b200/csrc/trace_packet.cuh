@@ -38,11 +38,13 @@ constexpr int PK_WARPS = PK_THREADS / 32;
 #ifndef PK_MIN_BLOCKS_V
 #define PK_MIN_BLOCKS_V 6
 #endif
-constexpr int PK_MIN_BLOCKS = PK_MIN_BLOCKS_V;   // register budget: 65536 / (6 * 128) = 85
+constexpr int PK_MIN_BLOCKS = PK_MIN_BLOCKS_V;   // hit lists, PROF, WIDE: 65536 / (6 * 128) = 85 registers; the
+                                                 // other modes ask for 7 CTAs (72 registers), see the kernel
 #ifndef PK_STACK_V
 #define PK_STACK_V 192
 #endif
-constexpr int PK_STACK = PK_STACK_V;  // reference STACK_SIZE is 64 (kernel_config.h:13)
+constexpr int PK_STACK = PK_STACK_V;  // reference STACK_SIZE is 64 (kernel_config.h:13); 192 entries x 8 B is
+                                      // what still lets 7 column-density CTAs fit in 228 KB of shared memory
 #ifndef PK_DFS_RESERVE_V
 #define PK_DFS_RESERVE_V 64
 #endif
