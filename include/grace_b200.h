@@ -166,7 +166,9 @@ typedef struct {
  *     staged leaves and deferred on-hit work; the hit set is exactly the brute-force set.
  *  PACKET_WIDE: the same leaf work, but inner nodes are culled against a conservative bound
  *     of the whole packet, 32 nodes at a time (one per lane), instead of one node per step
- *     with 32 slab tests; per-ray slab tests are made on leaf boxes only.
+ *     with 32 slab tests; per-ray slab tests are made on leaf boxes only.  EXPERIMENTAL: same
+ *     results, but its stack-bounded expansion degenerates on very heavy packets (several times
+ *     slower than PACKET on clustered data); kept for A/B measurements only.
  *  PER_RAY: every lane walks the tree for its own ray (padded slab test).
  *  PACKET_REF: the reference's schedule and slab arithmetic bit for bit; defines the
  *     traversal counters of grace_b200_trace_stats_f4. */
