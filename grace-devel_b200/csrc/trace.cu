@@ -604,7 +604,9 @@ int launch_packet(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, int n_packe
             T.eager = (ctx->trace_budget & GRACE_B200_BUDGET_EAGER) ? 1 : 0;
             // Round 0 whose children (32/8 per packet) would all fit on idle warps: split on the
             // budget alone.  Otherwise a unit must also be heavier than the launch's running mean.
-            const bool roomy = round == 0 && (size_t)n_packets * (32 / widths[0]) <= (size_t)full_grid * PK_WARPS;
+            // (3/4 of the slots: measured at 2^24 particles, 512 packets want the budget rule -- 6.8 vs
+            // 12 ms -- and 1024 packets the mean rule -- 10.5 vs 14.4 ms -- on 3552 and on 4144 warp slots)
+            const bool roomy = round == 0 && 4 * (size_t)n_packets * (32 / widths[0]) <= 3 * (size_t)full_grid * PK_WARPS;
             T.sum_steps = (unsigned long long*)(n_counts + 4); T.n_done = roomy ? nullptr : n_counts + 6;
             if (round > 0) GB_CUDA(cudaMemsetAsync(n_counts + 4, 0, 3 * sizeof(int), st));        // per-round statistics
             if (round > 0) { T.tasks_in = lists[(round - 1) & 1]; T.n_tasks_in = n_counts + 1 + ((round - 1) & 1); }
