@@ -32,7 +32,7 @@ __all__ = [
     "uniform_random_rays", "uniform_random_rays_single_octant", "one_to_many_rays",
     "plane_parallel_random_rays", "orthographic_projection_rays", "pinhole_camera_rays",
     "healpix_rays", "synth_gadget_spheres", "exclusive_segmented_scan",
-    "weighted_exclusive_segmented_scan", "offsets_to_segments", "read_gadget", "write_gadget", "gadget_info", "context", "lib", "build_tree", "set_trace_mode", "set_trace_budget", "set_trace_dynamic", "set_trace_resume", "device_error", "sharded_trace", "tiles_of_rank",
+    "weighted_exclusive_segmented_scan", "offsets_to_segments", "read_gadget", "write_gadget", "gadget_info", "context", "lib", "build_tree", "set_trace_mode", "set_trace_budget", "set_trace_pool", "trace_balance_stats", "device_error", "sharded_trace", "tiles_of_rank",
 ]
 
 _c = ctypes
@@ -180,7 +180,7 @@ def set_trace_mode(mode):
     """'packet' (default), 'ray' (per-ray traversal) or 'packet_ref' (the reference's
     schedule and slab arithmetic bit for bit); see include/grace_b200.h."""
     _check(_sig("grace_b200_set_trace_mode", [_P, _c.c_int])(
-        context(), {"ray": 0, "packet": 1, "packet_ref": 2, "packet_wide": 3}[mode]))
+        context(), {"ray": 0, "packet": 1, "packet_ref": 2}[mode]))
 
 
 def set_trace_budget(steps, eager=False):
@@ -189,12 +189,16 @@ def set_trace_budget(steps, eager=False):
     _check(_sig("grace_b200_set_trace_budget", [_P, _c.c_int])(context(), int(steps) | ((1 << 30) if eager else 0)))
 
 
-def set_trace_resume(per_ray):
-    _check(_sig("grace_b200_set_trace_resume", [_P, _c.c_int])(context(), int(bool(per_ray))))
+def set_trace_pool(nbytes):
+    """Workspace for the per-hit terms recorded by column-density tasks (0 = automatic)."""
+    _check(_sig("grace_b200_set_trace_pool", [_P, _sz])(context(), int(nbytes)))
 
 
-def set_trace_dynamic(on):
-    _check(_sig("grace_b200_set_trace_dynamic", [_P, _c.c_int])(context(), int(bool(on))))
+def trace_balance_stats():
+    """Diagnostic: work-stealing counters of the last hit-count / column-density call."""
+    out = (_c.c_int * 8)()
+    _check(_sig("grace_b200_trace_balance_stats", [_P, _P, _P])(context(), out, _stream()))
+    return dict(finished=out[0], tasks=out[1], chunks=out[5], robbed=out[6])
 
 
 def device_error():

@@ -480,24 +480,36 @@ int grid_cap(const grace_b200_ctx* ctx, size_t work_items, int per_block, int pe
     return (int)blocks;
 }
 
+// Workspace of one build: leaf-level deltas, per-node arrival flags, look-back states.
 template <typename T>
-int build_typed(grace_b200_ctx* ctx, const float4* d_spheres, size_t n, const T* d_deltas,
-                int mpl, int4* d_nodes, int4* d_leaves, int* d_root, cudaStream_t st, bool from_aabb = false)
+struct BuildWs { T* leaf_deltas; unsigned* flags; unsigned long long* block_state; };
+
+template <typename T>
+int build_workspace(grace_b200_ctx* ctx, size_t n, BuildWs<T>* out)
 {
-    const int n_nodes = (int)n - 1;
-    const int lv_blocks = (n_nodes + LV_TILE - 1) / LV_TILE;
+    const int lv_blocks = ((int)n - 1 + LV_TILE - 1) / LV_TILE;
     const size_t bytes = gb_align((n + 1) * sizeof(T)) + gb_align(n * sizeof(unsigned)) +
                          gb_align((size_t)lv_blocks * 8) + 256;
     void* ws = gb_workspace(ctx, bytes);
     if (!ws) return GRACE_B200_ENOMEM;
     GbArena a(ws, bytes);
-    T* leaf_deltas = a.take<T>(n + 1);
-    unsigned* flags = a.take<unsigned>(n);
-    unsigned long long* block_state = a.take<unsigned long long>(lv_blocks);
+    out->leaf_deltas = a.take<T>(n + 1);
+    out->flags = a.take<unsigned>(n);
+    out->block_state = a.take<unsigned long long>(lv_blocks);
+    return GRACE_B200_OK;
+}
+
+// Stage 1 (build_leaves + remove_empty_leaves + copy_leaf_deltas): dense leaves, their count in
+// d_scalars[GB_SC_NLEAVES], leaf-level deltas and zeroed arrival flags in the workspace.
+template <typename T>
+int leaves_stage(grace_b200_ctx* ctx, size_t n, const T* d_deltas, int mpl, int4* d_leaves, const BuildWs<T>& w,
+                 cudaStream_t st)
+{
+    const int n_nodes = (int)n - 1;
+    const int lv_blocks = (n_nodes + LV_TILE - 1) / LV_TILE;
     unsigned* ticket = (unsigned*)(ctx->d_scalars + GB_SC_TICKET1);
     int* d_nleaves = ctx->d_scalars + GB_SC_NLEAVES;
-
-    GB_CUDA(cudaMemsetAsync(block_state, 0, (size_t)lv_blocks * 8, st));
+    GB_CUDA(cudaMemsetAsync(w.block_state, 0, (size_t)lv_blocks * 8, st));
     GB_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
     // table levels: 2^K > mpl; the table must fit in shared memory
     int K = 0;
@@ -506,8 +518,8 @@ int build_typed(grace_b200_ctx* ctx, const float4* d_spheres, size_t n, const T*
     const size_t level_words = wn + wn / 32 + 2;
     auto launch = [&](auto kernel, size_t smem) -> int {
         GB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kernel<<<lv_blocks, LV_THREADS, smem, st>>>(d_deltas, (int)n, mpl, d_leaves, leaf_deltas, flags,
-                                                    block_state, ticket, d_nleaves);
+        kernel<<<lv_blocks, LV_THREADS, smem, st>>>(d_deltas, (int)n, mpl, d_leaves, w.leaf_deltas, w.flags,
+                                                    w.block_state, ticket, d_nleaves);
         return GRACE_B200_OK;
     };
     int lrc;
@@ -517,18 +529,38 @@ int build_typed(grace_b200_ctx* ctx, const float4* d_spheres, size_t n, const T*
     else lrc = launch(leaves_kernel<T, false, 0>, 0);
     if (lrc) return lrc;
     GB_LAUNCH_CHECK();
-    // The leaf count is only known on the device (anything up to n): warps stride over
-    // 32-leaf windows.
-    const int nd_blocks = grid_cap(ctx, n, ND_THREADS, 8);
+    return GRACE_B200_OK;
+}
+
+// Stage 2 (build_nodes): `cap` bounds the leaf count, which is read on the device (d_nleaves).
+template <typename T>
+int nodes_stage(grace_b200_ctx* ctx, const float4* d_prims, bool from_aabb, size_t cap, const int4* d_leaves,
+                const int* d_nleaves, const T* leaf_deltas, unsigned* flags, int4* d_nodes, int* d_root, cudaStream_t st)
+{
+    // warps stride over 32-leaf windows
+    const int nd_blocks = grid_cap(ctx, cap, ND_THREADS, 8);
     if (from_aabb)
-        nodes_kernel<T, true><<<nd_blocks, ND_THREADS, 0, st>>>(d_spheres, d_leaves, d_nleaves, leaf_deltas,
-                                                                 d_nodes, flags, d_root);
+        nodes_kernel<T, true><<<nd_blocks, ND_THREADS, 0, st>>>(d_prims, d_leaves, d_nleaves, leaf_deltas, d_nodes, flags, d_root);
     else
-        nodes_kernel<T, false><<<nd_blocks, ND_THREADS, 0, st>>>(d_spheres, d_leaves, d_nleaves, leaf_deltas,
-                                                                  d_nodes, flags, d_root);
+        nodes_kernel<T, false><<<nd_blocks, ND_THREADS, 0, st>>>(d_prims, d_leaves, d_nleaves, leaf_deltas, d_nodes, flags, d_root);
     GB_LAUNCH_CHECK();
     return GRACE_B200_OK;
 }
+
+template <typename T>
+int build_typed(grace_b200_ctx* ctx, const float4* d_spheres, size_t n, const T* d_deltas,
+                int mpl, int4* d_nodes, int4* d_leaves, int* d_root, cudaStream_t st, bool from_aabb = false)
+{
+    BuildWs<T> w;
+    int rc = build_workspace<T>(ctx, n, &w);
+    if (rc) return rc;
+    if ((rc = leaves_stage<T>(ctx, n, d_deltas, mpl, d_leaves, w, st))) return rc;
+    // the leaf count is only known on the device (anything up to n)
+    return nodes_stage<T>(ctx, d_spheres, from_aabb, n, d_leaves, ctx->d_scalars + GB_SC_NLEAVES, w.leaf_deltas, w.flags,
+                          d_nodes, d_root, st);
+}
+
+__global__ void set_int_kernel(int* p, int v) { *p = v; }
 
 int launch_simple(const grace_b200_ctx* ctx, size_t n) { return grid_cap(ctx, n + 1, 256, 16); }
 
@@ -621,6 +653,68 @@ int grace_b200_albvh_build_aabb(grace_b200_ctx* ctx, const float* d_aabbs8, size
 {
     return albvh_build_any(ctx, d_aabbs8, true, n, d_deltas, delta_type, max_per_leaf, d_nodes, d_leaves,
                            d_root, h_n_leaves, stream);
+}
+
+int grace_b200_albvh_leaves(grace_b200_ctx* ctx, const void* d_deltas, int delta_type, size_t n, int max_per_leaf,
+                            void* d_leaves, int* h_n_leaves, void* stream)
+{
+    GB_REQUIRE(ctx && d_deltas && d_leaves, GRACE_B200_EINVAL, "NULL argument");
+    GB_REQUIRE(max_per_leaf >= 1, GRACE_B200_EINVAL, "max_per_leaf must be >= 1");
+    // albvh.cuh:795-799
+    GB_REQUIRE(n > (size_t)max_per_leaf, GRACE_B200_EINVAL,
+               "max_per_leaf must be less than the total number of primitives.");
+    GB_REQUIRE(n < (1ull << 31) - 1024, GRACE_B200_ERANGE, "more than 2^31 primitives");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+#define GB_LEAVES_CASE(T)                                                                          \
+    { BuildWs<T> w;                                                                                \
+      if ((rc = build_workspace<T>(ctx, n, &w))) return rc;                                        \
+      rc = leaves_stage<T>(ctx, n, (const T*)d_deltas, max_per_leaf, (int4*)d_leaves, w, st); }
+    if (delta_type == GRACE_B200_DELTA_F32) GB_LEAVES_CASE(float)
+    else if (delta_type == GRACE_B200_DELTA_U32) GB_LEAVES_CASE(uint32_t)
+    else if (delta_type == GRACE_B200_DELTA_U64) GB_LEAVES_CASE(uint64_t)
+    else return gb_set_error(GRACE_B200_EINVAL, "unknown delta_type %d", delta_type);
+#undef GB_LEAVES_CASE
+    if (rc) return rc;
+    if (h_n_leaves) return grace_b200_albvh_last_n_leaves(ctx, h_n_leaves, stream);
+    return GRACE_B200_OK;
+}
+
+static int albvh_nodes_any(grace_b200_ctx* ctx, const float* d_prims, bool from_aabb, const void* d_leaves,
+                           size_t n_leaves, const void* d_leaf_deltas, int delta_type, void* d_nodes, int* d_root,
+                           void* stream)
+{
+    GB_REQUIRE(ctx && d_prims && d_leaves && d_leaf_deltas && d_nodes && d_root, GRACE_B200_EINVAL, "NULL argument");
+    GB_REQUIRE(n_leaves >= 2 && n_leaves < (1ull << 31) - 1024, GRACE_B200_EINVAL, "a tree needs at least two leaves");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned* flags = (unsigned*)gb_workspace(ctx, gb_align(n_leaves * sizeof(unsigned)) + 256);
+    if (!flags) return GRACE_B200_ENOMEM;
+    GB_CUDA(cudaMemsetAsync(flags, 0, n_leaves * sizeof(unsigned), st));
+    int* d_nleaves = ctx->d_scalars + GB_SC_NLEAVES;
+    set_int_kernel<<<1, 1, 0, st>>>(d_nleaves, (int)n_leaves);
+    GB_LAUNCH_CHECK();
+    if (delta_type == GRACE_B200_DELTA_F32)
+        return nodes_stage<float>(ctx, (const float4*)d_prims, from_aabb, n_leaves, (const int4*)d_leaves, d_nleaves,
+                                  (const float*)d_leaf_deltas, flags, (int4*)d_nodes, d_root, st);
+    if (delta_type == GRACE_B200_DELTA_U32)
+        return nodes_stage<uint32_t>(ctx, (const float4*)d_prims, from_aabb, n_leaves, (const int4*)d_leaves, d_nleaves,
+                                     (const uint32_t*)d_leaf_deltas, flags, (int4*)d_nodes, d_root, st);
+    if (delta_type == GRACE_B200_DELTA_U64)
+        return nodes_stage<uint64_t>(ctx, (const float4*)d_prims, from_aabb, n_leaves, (const int4*)d_leaves, d_nleaves,
+                                     (const uint64_t*)d_leaf_deltas, flags, (int4*)d_nodes, d_root, st);
+    return gb_set_error(GRACE_B200_EINVAL, "unknown delta_type %d", delta_type);
+}
+
+int grace_b200_albvh_nodes_f4(grace_b200_ctx* ctx, const float* d_spheres4, const void* d_leaves, size_t n_leaves,
+                              const void* d_leaf_deltas, int delta_type, void* d_nodes, int* d_root, void* stream)
+{
+    return albvh_nodes_any(ctx, d_spheres4, false, d_leaves, n_leaves, d_leaf_deltas, delta_type, d_nodes, d_root, stream);
+}
+
+int grace_b200_albvh_nodes_aabb(grace_b200_ctx* ctx, const float* d_aabbs8, const void* d_leaves, size_t n_leaves,
+                                const void* d_leaf_deltas, int delta_type, void* d_nodes, int* d_root, void* stream)
+{
+    return albvh_nodes_any(ctx, d_aabbs8, true, d_leaves, n_leaves, d_leaf_deltas, delta_type, d_nodes, d_root, stream);
 }
 
 int grace_b200_albvh_last_n_leaves(grace_b200_ctx* ctx, int* h_n_leaves, void* stream)

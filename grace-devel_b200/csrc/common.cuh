@@ -19,9 +19,8 @@ struct grace_b200_ctx {
     int* h_pinned = nullptr;   // pinned host mirror for count read-backs
     int last_n_leaves_valid = 0;
     int trace_mode = GRACE_B200_TRACE_PACKET;
-    int trace_budget = 1024;   // traversal steps before a packet may be split (0 = never)
-    int trace_dynamic = 0;     // 1: suspended traversals are resumed inside the same launch
-    int trace_resume_per_ray = 0;   // 1: suspended packets continue one ray per lane (second launch)
+    int trace_budget = 64;     // traversal steps before a unit may donate / be suspended (0 = never)
+    size_t trace_pool_bytes = 0;    // term pool of the column-density load balancing (0 = sized from the ray count)
     // file-loader staging (gadget_io.cu): two pinned host buffers + completion events, kept
     char* stage_host[2] = { nullptr, nullptr };
     size_t stage_bytes = 0;
@@ -38,7 +37,9 @@ enum {
     GB_SC_TOTAL64 = 8,      // 64-bit total (2 ints), 8-byte aligned
     GB_SC_TASKS = 32,       // trace load balancing: record count + two task-list counts
     GB_SC_CLASS = 40,       // segmented sort class counters (16 ints) + XL total (2 ints, 8-byte aligned)
-    GB_SC_COUNT = 64
+    GB_SC_LB = 64,          // trace work donation: {finished, tail, head, idle} (one 16-byte load), then
+                            // [4] records, [5] chunks taken, [6] root records
+    GB_SC_COUNT = 96
 };
 
 int gb_set_error(int code, const char* fmt, ...);

@@ -383,8 +383,15 @@ int grace_b200_trace_hits_count_f4(grace_b200_ctx* ctx, const grace_b200_ray* d_
     if (rc) return rc;
     long long* h_total = (long long*)(ctx->h_pinned + GB_SC_TOTAL64);
     GB_CUDA(cudaMemcpyAsync(h_total, d_total, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    // the traversal's error flag rides on the same synchronisation: counts from a walk that overflowed
+    // its stack or did not terminate are short, and the fill pass would disagree with them
+    GB_CUDA(cudaMemcpyAsync(ctx->h_pinned + GB_SC_ERRFLAG, ctx->d_scalars + GB_SC_ERRFLAG, sizeof(int),
+                            cudaMemcpyDeviceToHost, st));
     GB_CUDA(cudaStreamSynchronize(st));
     *h_total_hits = *h_total;
+    GB_REQUIRE(ctx->h_pinned[GB_SC_ERRFLAG] == 0, GRACE_B200_EDEVICE,
+               "device-side traversal error %d (1 = stack overflow, 2 = walk did not terminate): hit counts are incomplete",
+               ctx->h_pinned[GB_SC_ERRFLAG]);
     // trace_sph.cuh:117,137: offsets and totals are int in the reference
     GB_REQUIRE(*h_total_hits <= 0x7fffffffLL, GRACE_B200_ERANGE,
                "%lld hits exceed the 32-bit offsets of the reference layout; tile the rays",

@@ -426,81 +426,6 @@ trace_ray_kernel(const grace_b200_ray* __restrict__ rays, int n_packets,
 
 #include "trace_packet.cuh"
 
-// ---------------------------------------------------------------------------
-// Per-ray continuation of suspended packets.
-//
-// A packet suspended by trace_packet_kernel (heavy tail of the launch) is resumed here with one
-// ray per lane: every lane rebuilds ITS OWN stack from the packet's {node, lane mask} entries and
-// walks on alone (rt_walk), so all 32 lanes stay busy whatever their rays do, where ray-subset
-// tasks of the packet kernel keep only 8, 2 or 1 lanes of a warp busy and walk the shared part
-// of the tree once per task.  Left-first depth-first order is kept, so every ray still meets
-// its primitives in ascending index order: results are bit-identical.
-// ---------------------------------------------------------------------------
-template <int MODE>
-__global__ void __launch_bounds__(RT_THREADS)
-trace_ray_resume_kernel(const PkArgs P, const int* __restrict__ records, const int* __restrict__ n_records_ptr,
-                        const int records_cap)
-{
-    __shared__ double s_table[52];
-    __shared__ int s_stack[RT_SMEM_DEPTH * RT_THREADS];
-    const int lane = threadIdx.x & 31;
-    if (MODE == MODE_CUMULATIVE || MODE == MODE_FILL) {
-        for (int i = threadIdx.x; i < N_TABLE; i += RT_THREADS) s_table[i] = c_kernel_table[i];
-        __syncthreads();
-    }
-    int* my_stack = s_stack + threadIdx.x;
-    int lstack[RT_LOCAL_DEPTH];
-    const int n_rec = min(__ldg(n_records_ptr), records_cap);
-    for (;;) {
-        int unit = 0;
-        if (lane == 0) unit = atomicAdd(P.unit_counter, 1);
-        unit = __shfl_sync(0xffffffffu, unit, 0);
-        if (unit >= n_rec) break;
-        const int* rec = records + (size_t)unit * PK_REC_WORDS;
-        const int packet = rec[0];
-        const unsigned subset = (unsigned)rec[1];
-        const int sp_pk = rec[2], top = rec[3];
-        const unsigned top_mask = (unsigned)rec[4];
-        const bool mine = (subset >> lane) & 1u;
-        const int ray_index = packet * 32 + lane;
-        const grace_b200_ray ray = P.rays[ray_index];
-        RtRay R;
-        R.ix = __fdiv_rn(1.0f, ray.dx); R.iy = __fdiv_rn(1.0f, ray.dy); R.iz = __fdiv_rn(1.0f, ray.dz);
-        const float pad = 64.0f * 5.9604645e-8f * (fabsf(ray.ox) + fabsf(ray.oy) + fabsf(ray.oz) + fabsf(ray.length));
-        R.lox = ray.ox + pad; R.loy = ray.oy + pad; R.loz = ray.oz + pad;
-        R.hix = ray.ox - pad; R.hiy = ray.oy - pad; R.hiz = ray.oz - pad;
-        float cum = __int_as_float(rec[8 + 2 * PK_STACK + lane]);
-        int count = rec[8 + 2 * PK_STACK + 32 + lane];
-        int cursor = rec[8 + 2 * PK_STACK + 64 + lane];
-        // this lane's stack: the packet's entries (bottom to top) whose mask holds the lane
-        int sp = 0;
-        const int2* pk_stack = (const int2*)(rec + 8);
-        for (int i = 0; i < sp_pk; ++i) {
-            const int2 e = pk_stack[i];
-            if (mine && (((unsigned)e.y >> lane) & 1u)) {
-                if (sp < RT_SMEM_DEPTH) my_stack[sp * RT_THREADS] = e.x;
-                else if (sp < RT_SMEM_DEPTH + RT_LOCAL_DEPTH) lstack[sp - RT_SMEM_DEPTH] = e.x;
-                else *P.err_flag = 1;
-                ++sp;
-            }
-        }
-        int cur = -1;
-        if (mine) {
-            if (top >= 0 && ((top_mask >> lane) & 1u)) cur = top;
-            else if (sp > 0) {
-                --sp;
-                cur = sp < RT_SMEM_DEPTH ? my_stack[sp * RT_THREADS] : lstack[min(sp - RT_SMEM_DEPTH, RT_LOCAL_DEPTH - 1)];
-            }
-        }
-        rt_walk<MODE>(cur, sp, my_stack, lstack, ray, R, P.spheres, P.nodes, P.leaves, P.n_nodes, P.err_flag, s_table,
-                      P.hit_idx, P.hit_integral, P.hit_dist, count, cum, cursor);
-        if (mine) {
-            if (MODE == MODE_COUNT) P.out_counts[ray_index] = count;
-            if (MODE == MODE_CUMULATIVE) P.out_cum[ray_index] = cum;
-        }
-    }
-}
-
 size_t trace_smem_bytes(int max_per_leaf)
 {
     return 52 * sizeof(double) + (size_t)TR_WARPS * TR_STACK * sizeof(int) +
@@ -515,12 +440,11 @@ int launch_packet(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, int n_packe
 {
     if (MODE == MODE_STATS || MODE == MODE_RAYCOST) return GRACE_B200_EINVAL;   // other kernels
     constexpr int KMODE = (MODE == MODE_STATS || MODE == MODE_RAYCOST) ? MODE_COUNT : MODE;
+    constexpr bool SUB = KMODE != MODE_FILL;          // subtree donation inside the launch (counts, column densities)
+    constexpr bool CHAIN = KMODE == MODE_CUMULATIVE;  // ordered term chains + fold launch
     // the per-packet profile counters exist only in a separate MODE_COUNT instantiation
-    const bool wide = ctx->trace_mode == GRACE_B200_TRACE_PACKET_WIDE;
-    auto kernel = (KMODE == MODE_COUNT && d_prof)
-                      ? (wide ? trace_packet_kernel<KMODE, M4, KMODE == MODE_COUNT, true>
-                              : trace_packet_kernel<KMODE, M4, KMODE == MODE_COUNT, false>)
-                      : (wide ? trace_packet_kernel<KMODE, M4, false, true> : trace_packet_kernel<KMODE, M4, false, false>);
+    auto kernel = (KMODE == MODE_COUNT && d_prof) ? trace_packet_kernel<KMODE, M4, KMODE == MODE_COUNT>
+                                                  : trace_packet_kernel<KMODE, M4, false>;
     constexpr size_t psmem = packet_smem_bytes<KMODE, M4>();
     GB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
     int per_sm = 0;
@@ -531,25 +455,10 @@ int launch_packet(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, int n_packe
     const int need = (n_packets + PK_WARPS - 1) / PK_WARPS;
     if (blocks > need) blocks = need;
     int* counter = ctx->d_scalars + GB_SC_TRACE_CTR;
-    // Load balancing rounds: 0 = packets, then suspended traversals resumed as tasks over
-    // 8, 2 and finally 1 ray(s); the last round runs to completion.  Rounds with nothing to
-    // do cost one empty launch.  Disabled (single round) for the profile counters.
-    const bool split = (d_prof == nullptr) && (ctx->trace_budget & 0x3fffffff) > 0 && n_packets >= 64;
-    const int records_cap = split ? (int)std::min<size_t>(std::max<size_t>((size_t)n_packets / 4, 1024), 32768) : 0;
-    const int tasks_cap = 4 * records_cap;
-    int* records = nullptr;
-    int2* lists[2] = { nullptr, nullptr };
-    if (split) {
-        const size_t rec_bytes = gb_align((size_t)records_cap * PK_REC_WORDS * 4);
-        const size_t list_bytes = gb_align((size_t)tasks_cap * 8);
-        char* w = (char*)gb_workspace(ctx, 4096 + rec_bytes + 2 * list_bytes);
-        if (!w) return GRACE_B200_ENOMEM;
-        records = (int*)(w + 4096);
-        lists[0] = (int2*)(w + 4096 + rec_bytes);
-        lists[1] = (int2*)(w + 4096 + rec_bytes + list_bytes);
-    }
-    int* n_counts = ctx->d_scalars + GB_SC_TASKS;      // [0] records, [1] list 0, [2] list 1
-    if (split) GB_CUDA(cudaMemsetAsync(n_counts, 0, 8 * sizeof(int), st));     // + [4,5] step sum (64-bit), [6] units done
+    // Load balancing (disabled for the profile counters).  Counts, column densities: one launch in which
+    // units donate subtrees to idle warps, + the fold launch for column densities.  Hit lists: four
+    // launches, 0 = packets, then suspended traversals resumed as tasks over 8, 2 and finally 1 ray(s).
+    const bool split = (d_prof == nullptr) && (ctx->trace_budget & 0x3fffffff) > 0 && n_packets >= 2;
     GB_CUDA(cudaMemsetAsync(ctx->d_scalars + GB_SC_ERRFLAG, 0, sizeof(int), st));
     PkArgs P;
     P.rays = d_rays; P.n_packets = n_packets; P.spheres = (const float4*)d_spheres4;
@@ -558,63 +467,103 @@ int launch_packet(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, int n_packe
     P.out_counts = out_counts; P.out_cum = out_cum; P.offsets = offsets;
     P.hit_idx = hit_idx; P.hit_integral = hit_integral; P.hit_dist = hit_dist;
     P.unit_counter = counter; P.err_flag = ctx->d_scalars + GB_SC_ERRFLAG; P.prof = d_prof;
-    const int widths[3] = { 8, 2, 1 };
-    if (split && ctx->trace_dynamic) {
-        // One launch: suspended traversals go to a queue that the idle warps of the same launch drain.
+    if (!split) {
         PkTasks T = {};
-        T.records = records; T.n_records = n_counts; T.records_cap = records_cap;
-        T.budget = ctx->trace_budget & 0x3fffffff;
-        T.eager = (ctx->trace_budget & GRACE_B200_BUDGET_EAGER) ? 1 : 0;
-        T.dynamic = 1;
-        T.sum_steps = (unsigned long long*)(n_counts + 4); T.n_done = n_counts + 6;
-        T.queue = lists[0]; T.queue_cap = 2 * tasks_cap;        // lists[0] and lists[1] are contiguous
-        T.q_head = n_counts + 1; T.q_tail = n_counts + 2; T.finished = n_counts + 3;
-        GB_CUDA(cudaMemsetAsync(T.queue, 0xff, (size_t)T.queue_cap * 8, st));    // slot.x = -1: not published
-        GB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
-        kernel<<<full_grid, PK_THREADS, psmem, st>>>(P, T);
-        GB_LAUNCH_CHECK();
-        return GRACE_B200_OK;
-    }
-    if (split && ctx->trace_resume_per_ray && !wide) {
-        // Round 0: packets; the heavy ones still running when the queue drains are suspended whole.
-        // Round 1: their rays continue one per lane (trace_ray_resume_kernel).
-        PkTasks T = {};
-        T.records = records; T.n_records = n_counts; T.records_cap = records_cap; T.tasks_cap = tasks_cap;
-        T.budget = ctx->trace_budget & 0x3fffffff;
-        T.eager = (ctx->trace_budget & GRACE_B200_BUDGET_EAGER) ? 1 : 0;
-        T.tasks_out = lists[0]; T.n_tasks_out = n_counts + 1; T.child_width = 32;
-        T.sum_steps = (unsigned long long*)(n_counts + 4); T.n_done = n_counts + 6;
+        T.kind = PK_KIND_PACKETS;
         GB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
         kernel<<<blocks, PK_THREADS, psmem, st>>>(P, T);
         GB_LAUNCH_CHECK();
-        int rper = 0;
-        GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&rper, trace_ray_resume_kernel<KMODE>, RT_THREADS, 0));
-        if (rper < 1) rper = 1;
-        GB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
-        trace_ray_resume_kernel<KMODE><<<ctx->sm_count * rper, RT_THREADS, 0, st>>>(P, records, n_counts, records_cap);
-        GB_LAUNCH_CHECK();
         return GRACE_B200_OK;
     }
-    const int n_rounds = split ? 4 : 1;
+    if (SUB) {
+        // work stealing inside one launch: one slot per resident warp, theft records, roots, term pool
+        const int n_slots = full_grid * PK_WARPS;
+        const int records_cap = 1 << 20;
+        const size_t rec_bytes = gb_align((size_t)records_cap * PK_DREC_WORDS * 4);
+        const size_t slot_bytes = gb_align((size_t)n_slots * sizeof(int));
+        const size_t roots_bytes = CHAIN ? gb_align((size_t)n_packets * sizeof(int2)) : 0;
+        const size_t rcum_bytes = CHAIN ? gb_align((size_t)n_packets * 32 * sizeof(float)) : 0;
+        // term pool: the terms of stolen work only -- at most the hits of the packets in flight when the
+        // tickets run out, i.e. bounded by the grid, not by the ray count.  A dry pool costs time (the
+        // fold launch walks the aborted tasks itself), never correctness.
+        size_t pool_bytes = 0;
+        int pool_cap = 0;
+        if (CHAIN) {
+            pool_bytes = ctx->trace_pool_bytes ? ctx->trace_pool_bytes
+                                               : std::min<size_t>(std::max<size_t>((size_t)n_packets * 32 * 65536, (size_t)64 << 20),
+                                                                  (size_t)2048 << 20);
+            pool_cap = (int)std::min<size_t>(pool_bytes / PK_CH_BYTES, 1u << 30);
+            pool_bytes = gb_align((size_t)pool_cap * PK_CH_BYTES);
+        }
+        const size_t adv_bytes = gb_align(PK_ADV * sizeof(int));
+        char* w = (char*)gb_workspace(ctx, 4096 + rec_bytes + 2 * slot_bytes + adv_bytes + roots_bytes + rcum_bytes + pool_bytes);
+        if (!w) return GRACE_B200_ENOMEM;
+        int* lb = ctx->d_scalars + GB_SC_LB;
+        PkTasks T = {};
+        T.kind = PK_KIND_PACKETS;
+        char* p = w + 4096;
+        T.records = (int*)p; p += rec_bytes;
+        T.state = (int*)p; p += slot_bytes;
+        T.resp = (int*)p; p += slot_bytes;
+        T.adv = (int*)p; p += adv_bytes;
+        T.roots = (int2*)p; p += roots_bytes;
+        T.root_cum = (float*)p; p += rcum_bytes;
+        T.pool = CHAIN ? p : nullptr;
+        T.n_slots = n_slots;
+        T.records_cap = records_cap;
+        T.budget = ctx->trace_budget & 0x3fffffff;
+        T.eager = (ctx->trace_budget & GRACE_B200_BUDGET_EAGER) ? 1 : 0;
+        T.lb = lb;
+        T.n_roots = lb + 6;
+        T.pool_ctr = lb + 5; T.pool_cap = pool_cap;
+        GB_CUDA(cudaMemsetAsync(lb, 0, 8 * sizeof(int), st));
+        GB_CUDA(cudaMemsetAsync(T.state, 0, slot_bytes, st));         // nobody walking
+        GB_CUDA(cudaMemsetAsync(T.adv, 0, adv_bytes, st));
+        GB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
+        // robbed packets and their tasks add into the same cells
+        if (KMODE == MODE_COUNT) GB_CUDA(cudaMemsetAsync(out_counts, 0, (size_t)n_packets * 32 * sizeof(int), st));
+        // the whole grid: the warps that get no packet are the first thieves
+        kernel<<<full_grid, PK_THREADS, psmem, st>>>(P, T);
+        GB_LAUNCH_CHECK();
+        if (CHAIN) {
+            T.kind = PK_KIND_FOLD;
+            T.state = nullptr;
+            GB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
+            kernel<<<full_grid, PK_THREADS, psmem, st>>>(P, T);
+            GB_LAUNCH_CHECK();
+        }
+        return GRACE_B200_OK;
+    }
+    const int records_cap = 16384, tasks_cap = 4 * records_cap;
+    const size_t rec_bytes = gb_align((size_t)records_cap * PK_REC_WORDS * 4);
+    // ---- hit lists: ray-subset rounds ----
+    const size_t list_bytes = gb_align((size_t)tasks_cap * 8);
+    char* w = (char*)gb_workspace(ctx, 4096 + rec_bytes + 2 * list_bytes);
+    if (!w) return GRACE_B200_ENOMEM;
+    int* records = (int*)(w + 4096);
+    int2* lists[2] = { (int2*)(w + 4096 + rec_bytes), (int2*)(w + 4096 + rec_bytes + list_bytes) };
+    int* n_counts = ctx->d_scalars + GB_SC_TASKS;      // [0] records, [1] list 0, [2] list 1, [4,5] step sum (64-bit), [6] units done
+    GB_CUDA(cudaMemsetAsync(n_counts, 0, 8 * sizeof(int), st));
+    const int widths[3] = { 8, 2, 1 };
+    const int n_rounds = 4;
     for (int round = 0; round < n_rounds; ++round) {
         PkTasks T = {};
-        if (split) {
-            T.records = records; T.n_records = n_counts; T.records_cap = records_cap; T.tasks_cap = tasks_cap;
-            T.budget = ctx->trace_budget & 0x3fffffff;
-            T.eager = (ctx->trace_budget & GRACE_B200_BUDGET_EAGER) ? 1 : 0;
-            // Round 0 whose children (32/8 per packet) would all fit on idle warps: split on the
-            // budget alone.  Otherwise a unit must also be heavier than the launch's running mean.
-            // (3/4 of the slots: measured at 2^24 particles, 512 packets want the budget rule -- 6.8 vs
-            // 12 ms -- and 1024 packets the mean rule -- 10.5 vs 14.4 ms -- on 3552 and on 4144 warp slots)
-            const bool roomy = round == 0 && 4 * (size_t)n_packets * (32 / widths[0]) <= 3 * (size_t)full_grid * PK_WARPS;
-            T.sum_steps = (unsigned long long*)(n_counts + 4); T.n_done = roomy ? nullptr : n_counts + 6;
-            if (round > 0) GB_CUDA(cudaMemsetAsync(n_counts + 4, 0, 3 * sizeof(int), st));        // per-round statistics
-            if (round > 0) { T.tasks_in = lists[(round - 1) & 1]; T.n_tasks_in = n_counts + 1 + ((round - 1) & 1); }
-            if (round < n_rounds - 1) {
-                T.tasks_out = lists[round & 1]; T.n_tasks_out = n_counts + 1 + (round & 1);
-                T.child_width = widths[round];
-                if (round >= 2) GB_CUDA(cudaMemsetAsync(T.n_tasks_out, 0, sizeof(int), st));   // list reuse
-            }
+        T.kind = round == 0 ? PK_KIND_PACKETS : PK_KIND_TASKS;
+        T.records = records; T.n_records = n_counts; T.records_cap = records_cap; T.tasks_cap = tasks_cap;
+        T.budget = ctx->trace_budget & 0x3fffffff;
+        T.eager = (ctx->trace_budget & GRACE_B200_BUDGET_EAGER) ? 1 : 0;
+        // Round 0 whose children (32/8 per packet) would all fit on idle warps: split on the budget
+        // alone.  Otherwise a unit must also be heavier than the launch's running mean.
+        // (3/4 of the slots: measured at 2^24 particles, 512 packets want the budget rule -- 6.8 vs
+        // 12 ms -- and 1024 packets the mean rule -- 10.5 vs 14.4 ms -- on 3552 and on 4144 warp slots)
+        const bool roomy = round == 0 && 4 * (size_t)n_packets * (32 / widths[0]) <= 3 * (size_t)full_grid * PK_WARPS;
+        T.sum_steps = (unsigned long long*)(n_counts + 4); T.n_done = roomy ? nullptr : n_counts + 6;
+        if (round > 0) GB_CUDA(cudaMemsetAsync(n_counts + 4, 0, 3 * sizeof(int), st));        // per-round statistics
+        if (round > 0) { T.tasks_in = lists[(round - 1) & 1]; T.n_tasks_in = n_counts + 1 + ((round - 1) & 1); }
+        if (round < n_rounds - 1) {
+            T.tasks_out = lists[round & 1]; T.n_tasks_out = n_counts + 1 + (round & 1);
+            T.child_width = widths[round];
+            if (round >= 2) GB_CUDA(cudaMemsetAsync(T.n_tasks_out, 0, sizeof(int), st));   // list reuse
         }
         GB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
         kernel<<<round == 0 ? blocks : full_grid, PK_THREADS, psmem, st>>>(P, T);
@@ -658,8 +607,7 @@ int launch_trace(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, size_t n_ray
         return GRACE_B200_OK;
     }
     if (MODE != MODE_STATS && MODE != MODE_RAYCOST &&
-        (ctx->trace_mode == GRACE_B200_TRACE_PACKET || ctx->trace_mode == GRACE_B200_TRACE_PACKET_WIDE) &&
-        tree->max_per_leaf <= 128) {
+        ctx->trace_mode == GRACE_B200_TRACE_PACKET && tree->max_per_leaf <= 128) {
         if (tree->max_per_leaf <= 32)
             return launch_packet<MODE, 32>(ctx, d_rays, n_packets, d_spheres4, tree, out_counts, out_cum,
                                            offsets, hit_idx, hit_integral, hit_dist, st, d_stats);
@@ -710,24 +658,39 @@ int grace_b200_set_trace_budget(grace_b200_ctx* ctx, int steps)
     return GRACE_B200_OK;
 }
 
-int grace_b200_set_trace_resume(grace_b200_ctx* ctx, int per_ray)
+#ifdef PK_DEBUG_LB
+extern "C" __attribute__((visibility("default"))) int grace_b200_debug_lb(unsigned long long* out32, int reset)
 {
-    GB_REQUIRE(ctx, GRACE_B200_EINVAL, "ctx is NULL");
-    ctx->trace_resume_per_ray = per_ray ? 1 : 0;
+    if (reset) {
+        unsigned long long init[32] = {};
+        init[4] = init[7] = ~0ull;
+        return (int)cudaMemcpyToSymbol(pk_dbg, init, sizeof(init));
+    }
+    return (int)cudaMemcpyFromSymbol(out32, pk_dbg, 32 * sizeof(unsigned long long));
+}
+#endif
+
+int grace_b200_trace_balance_stats(grace_b200_ctx* ctx, int* h_stats8, void* stream)
+{
+    GB_REQUIRE(ctx && h_stats8, GRACE_B200_EINVAL, "NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    GB_CUDA(cudaMemcpyAsync(ctx->h_pinned + GB_SC_LB, ctx->d_scalars + GB_SC_LB, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    GB_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < 8; ++i) h_stats8[i] = ctx->h_pinned[GB_SC_LB + i];
     return GRACE_B200_OK;
 }
 
-int grace_b200_set_trace_dynamic(grace_b200_ctx* ctx, int on)
+int grace_b200_set_trace_pool(grace_b200_ctx* ctx, size_t bytes)
 {
     GB_REQUIRE(ctx, GRACE_B200_EINVAL, "ctx is NULL");
-    ctx->trace_dynamic = on ? 1 : 0;
+    ctx->trace_pool_bytes = bytes;
     return GRACE_B200_OK;
 }
 
 int grace_b200_set_trace_mode(grace_b200_ctx* ctx, int mode)
 {
     GB_REQUIRE(ctx, GRACE_B200_EINVAL, "ctx is NULL");
-    GB_REQUIRE(mode == GRACE_B200_TRACE_PER_RAY || mode == GRACE_B200_TRACE_PACKET || mode == GRACE_B200_TRACE_PACKET_REF || mode == GRACE_B200_TRACE_PACKET_WIDE, GRACE_B200_EINVAL,
+    GB_REQUIRE(mode == GRACE_B200_TRACE_PER_RAY || mode == GRACE_B200_TRACE_PACKET || mode == GRACE_B200_TRACE_PACKET_REF, GRACE_B200_EINVAL,
                "unknown trace mode %d", mode);
     ctx->trace_mode = mode;
     return GRACE_B200_OK;
@@ -787,7 +750,7 @@ int grace_b200_trace_packet_profile_f4(grace_b200_ctx* ctx, const grace_b200_ray
     if (!d_prof) return GRACE_B200_ENOMEM;
     GB_CUDA(cudaMemsetAsync(d_prof, 0, prof_words * 8, st));
     const int saved = ctx->trace_mode;
-    if (saved != GRACE_B200_TRACE_PACKET_WIDE) ctx->trace_mode = GRACE_B200_TRACE_PACKET;
+    ctx->trace_mode = GRACE_B200_TRACE_PACKET;
     int rc = launch_trace<MODE_COUNT>(ctx, d_rays, n_rays, d_spheres4, n, tree, d_hit_counts, nullptr,
                                       nullptr, nullptr, nullptr, nullptr, st, d_prof);
     ctx->trace_mode = saved;

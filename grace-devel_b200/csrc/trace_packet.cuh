@@ -25,8 +25,16 @@
 //     where it would run on ~1 lane in 9: hits go to a per-lane FIFO in shared memory and
 //     are evaluated in batches.  FIFO order keeps each ray's accumulation in ascending
 //     primitive order, so sums are bit-identical to the reference's;
-//   * load balance: a packet that exceeds a step budget saves its state and is resumed, in
-//     a follow-up launch, as several tasks over disjoint subsets of its rays (PkTasks).
+//   * load balance: heavy packets are as wide as light ones (max/mean hits per lane of the
+//     heaviest packets: 1.04-1.3) but run 10-25x longer, so the work is split by SUBTREE, not
+//     by ray, and inside the launch, by work stealing: a warp without a packet picks the
+//     longest-running unit it can see and asks it for the bottom entry of its stack (the
+//     subtree it would reach last, the largest it holds), which it then walks for all 32
+//     rays.  Hit counts are order-free (atomic adds).  Column densities need each ray's terms
+//     in ascending primitive order: a task appends its {W, 1/h^2} terms to a chain of chunks
+//     and a second launch folds the chains in traversal order, one FFMA per term, exactly as
+//     the unsplit traversal would have (pk_fold_chain).  Hit lists keep the older ray-subset
+//     split over several launches (their write positions depend on the hits before them).
 //
 // All shared-memory addresses are compile-time offsets of one per-warp struct (the first
 // version derived them from the runtime max_per_leaf and ptxas re-derived them inside the
@@ -45,10 +53,6 @@ constexpr int PK_MIN_BLOCKS = PK_MIN_BLOCKS_V;   // hit lists, PROF, WIDE: 65536
 #endif
 constexpr int PK_STACK = PK_STACK_V;  // reference STACK_SIZE is 64 (kernel_config.h:13); 192 entries x 8 B is
                                       // what still lets 7 column-density CTAs fit in 228 KB of shared memory
-#ifndef PK_DFS_RESERVE_V
-#define PK_DFS_RESERVE_V 64
-#endif
-constexpr int PK_DFS_RESERVE = PK_DFS_RESERVE_V;   // stack slots the wide traversal never fills with a wide step
 constexpr int PK_QD = 8;             // FIFO depth per lane
 #ifndef PK_BATCH_V
 #define PK_BATCH_V 4
@@ -72,7 +76,21 @@ struct PkWarp {
     unsigned char cells[NEED_Q ? PK_QD * 32 : 4];   // occupied FIFO cells, slot-major (flush work list)
     int idx[NEED_I ? M4 : 4];                  // primitive index of the staged spheres
     float2 q2[NEED_I ? PK_QD * 32 : 2];        // FIFO {distance, index bits}
+    // term chain of a recording task (column densities, stolen subtrees): see pk_chain_append
+    int ch_on, ch_cur, ch_head, ch_fail;       // recording?  current / first chunk, pool exhausted
+    int ch_off;                                // bytes used in the current chunk
+    char* pool; int* pool_ctr; int pool_cap;
 };
+
+// Term chains.  A chunk is PK_CH_BYTES: a 32-byte header {int next; int bytes used; ...} followed
+// by blocks, one per FIFO flush: 32 count bytes (terms of lane 0..31) and then the terms {W, 1/h^2},
+// lane after lane, each lane's in emission (= ascending primitive) order.  Nothing is padded: a
+// task in which three of the 32 rays hit anything stores three rays' worth (a [row][lane] layout
+// took 6x the space on incoherent packets and a proportionally longer fold).  Chunks come from a
+// pool by atomic ticket.
+constexpr int PK_CH_BYTES = 16384;
+constexpr int PK_CH_HDR = 32;
+
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 {
@@ -139,10 +157,100 @@ __device__ __forceinline__ void pk_flush_eval(PkWarp<MODE, M4>& W, int qn, int l
     __syncwarp();
 }
 
+
+// Append the evaluated FIFO cells of all lanes to the unit's term chain as one block.
+template <int MODE, int M4>
+__device__ __forceinline__ void pk_chain_append(PkWarp<MODE, M4>& W, int qn, int lane)
+{
+    int incl = qn;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int first = incl - qn;
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;
+    const int size = 32 + 8 * total;
+    int cur = W.ch_cur, off = W.ch_off;
+    if (cur < 0 || off + size > PK_CH_BYTES) {
+        if (W.ch_fail) return;                   // pool exhausted earlier: the unit is about to abort
+        int id = -1;
+        if (lane == 0) { id = atomicAdd(W.pool_ctr, 1); if (id >= W.pool_cap) id = -1; }
+        id = __shfl_sync(0xffffffffu, id, 0);
+        if (id < 0) { if (lane == 0) W.ch_fail = 1; __syncwarp(); return; }
+        if (lane == 0) {
+            if (cur >= 0) *(int2*)(W.pool + (size_t)cur * PK_CH_BYTES) = make_int2(id, off);      // close and link
+            else W.ch_head = id;
+            W.ch_cur = id;
+        }
+        cur = id;
+        off = PK_CH_HDR;
+    }
+    char* blk = W.pool + (size_t)cur * PK_CH_BYTES + off;
+    ((unsigned char*)blk)[lane] = (unsigned char)qn;
+    float2* t = (float2*)(blk + 32) + first;
+#pragma unroll
+    for (int j = 0; j < PK_QD; ++j)
+        if (j < qn) t[j] = W.q[j * 32 + lane];
+    __syncwarp();
+    if (lane == 0) W.ch_off = off + size;
+}
+
+// Write the header of the last chunk (the unit is finished).
+template <int MODE, int M4>
+__device__ __forceinline__ void pk_chain_close(PkWarp<MODE, M4>& W, int lane)
+{
+    __syncwarp();
+    const int cur = W.ch_cur;
+    if (cur >= 0 && lane == 0) *(int2*)(W.pool + (size_t)cur * PK_CH_BYTES) = make_int2(-1, W.ch_off);
+}
+
+// Fold a finished chain into `cum`: each lane adds ITS terms in the order they were emitted,
+// one FFMA per term -- the arithmetic of pk_flush_cum, hence of the unsplit traversal.  Latency
+// is what matters here (a heavy ray's chain is walked by one warp): the next chunk is prefetched
+// into L2 as soon as its id is known, and a block's terms are requested together.
+__device__ __noinline__ float pk_fold_chain(const char* pool, int head, float cum, int lane)
+{
+    for (int c = head; c >= 0;) {
+        const char* ch = pool + (size_t)c * PK_CH_BYTES;
+        const int2 h = __ldcg((const int2*)ch);          // next, bytes used
+        if (h.x >= 0) {
+            const char* np = pool + (size_t)h.x * PK_CH_BYTES + lane * 128;
+#pragma unroll
+            for (int k = 0; k < PK_CH_BYTES / 4096; ++k) asm volatile("prefetch.global.L2 [%0];" :: "l"(np + k * 4096));
+        }
+        int off = PK_CH_HDR;
+        while (off < h.y) {
+            const int n = __ldcg((const unsigned char*)(ch + off) + lane);
+            int incl = n;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const float2* t = (const float2*)(ch + off + 32) + (incl - n);
+            float2 e[PK_QD];
+#pragma unroll
+            for (int j = 0; j < PK_QD; ++j) if (j < n) e[j] = __ldcg(t + j);
+#pragma unroll
+            for (int j = 0; j < PK_QD; ++j) if (j < n) cum = __fmaf_rn(e[j].x, e[j].y, cum);
+            off += 32 + 8 * __shfl_sync(0xffffffffu, incl, 31);
+        }
+        c = h.x;
+    }
+    return cum;
+}
+
 template <int MODE, int M4>
 __device__ __noinline__ float pk_flush_cum(PkWarp<MODE, M4>& W, int qn, float cum, int lane, unsigned lt, const double2* table)
 {
     pk_flush_eval<MODE, M4>(W, qn, lane, lt, table);
+    if (W.ch_on) {            // recording task: the terms go to the chain, the fold launch adds them
+        pk_chain_append<MODE, M4>(W, qn, lane);
+        __syncwarp();
+        return cum;
+    }
 #pragma unroll
     for (int j = 0; j < PK_QD; ++j)
         if (j < qn) { const float2 e = W.q[j * 32 + lane]; cum = __fmaf_rn(e.x, e.y, cum); }
@@ -281,32 +389,6 @@ __device__ __forceinline__ bool packet_may_hit(const PacketBound& B, const float
     const bool outside = d2 > R * R;
     const bool behind = (t + s.w + slack) < B.t0min;
     return !(outside || behind);
-}
-
-// Can any ray of the packet touch the axis-aligned box [b, t]?  Conservative: every point x of
-// the box is at least d - sum_k |qh_k| e_k from the axis (c = centre, e = half extents, q = the
-// perpendicular from the axis to c, d = |q|, qh = q / d), and the packet's radius at the box's
-// farthest axial coordinate bounds its radius everywhere in the box.  Evaluated without the
-// square root: d^2 - sum |q_k| e_k <= R d.
-__device__ __forceinline__ bool packet_may_hit_box(const PacketBound& B, float bx, float tx, float by, float ty,
-                                                   float bz, float tz)
-{
-    const float cx = 0.5f * (bx + tx), cy = 0.5f * (by + ty), cz = 0.5f * (bz + tz);
-    const float ex = 0.5f * (tx - bx), ey = 0.5f * (ty - by), ez = 0.5f * (tz - bz);
-    const float px = cx - B.ocx, py = cy - B.ocy, pz = cz - B.ocz;
-    const float t = px * B.ax + py * B.ay + pz * B.az;
-    const float qx = px - t * B.ax, qy = py - t * B.ay, qz = pz - t * B.az;
-    const float d2 = qx * qx + qy * qy + qz * qz;
-    const float te = fabsf(B.ax) * ex + fabsf(B.ay) * ey + fabsf(B.az) * ez;
-    const float se = fabsf(qx) * ex + fabsf(qy) * ey + fabsf(qz) * ez;
-    const float scale = fabsf(px) + fabsf(py) + fabsf(pz) + ex + ey + ez + B.r0;
-    const float slack = 4e-5f * scale;
-    const float R = B.r0 + fmaxf(0.0f, t + te - B.t0min) * B.tan_t + slack;
-    const float g = d2 - se - slack * scale;         // <= 0: the axis passes within the box's shadow
-    const bool outside = (g > 0.0f) && (g * g > R * R * d2 * 1.0001f);
-    const bool behind = (t + te + slack) < B.t0min;
-    const bool beyond = (t - te - slack) > B.tfar;
-    return !(outside || behind || beyond);            // NaN anywhere -> comparisons false -> kept
 }
 
 __device__ __forceinline__ float pk_finite_rcp(float d)
@@ -462,34 +544,75 @@ __device__ __forceinline__ void pk_leaf_sparse(PkWarp<MODE, M4>& W, unsigned mas
     }
 }
 
-// Suspended traversals (load balancing): a unit of work that has run `budget` steps saves its
-// state in a record and is resumed in the next launch as up to 32/child_width tasks, each
-// owning the rays of one aligned block of child_width lanes.  Every ray keeps accumulating in
-// the same (ascending primitive) order, so results do not depend on whether or where a
-// traversal was split.
-constexpr int PK_REC_WORDS = 8 + 2 * PK_STACK + 3 * 32;   // header | stack | cum, count, cursor
+// ---- load balancing -------------------------------------------------------------------------
+// Hit counts and column densities (SUB = true): work stealing inside the launch, thief-directed.
+// Every warp of the (persistent, fully resident) grid has a slot word `state` (0 = nothing to
+// steal, s > 0 = the steps its unit has run + 1, refreshed every PK_CHECK_EVERY steps, s < 0 = a
+// thief's request) and an answer cell `resp`.  A warp that finds no packet left becomes a thief: it samples a few hundred
+// slots, picks the unit that has run longest (cost is heavy-tailed: the longest-running unit is
+// the best guess for the one with most left) and turns that warp's slot word into its request with
+// one compare-and-swap.  The victim sees the request at its next check and hands over the BOTTOM
+// entry of its stack -- the subtree it would reach last, the largest it holds -- as a task for all
+// rays of the unit, or answers "nothing" if it holds no subtree worth a task.  There is no shared
+// queue and no counter everybody fights over (a first version with a global task queue lost 99 %
+// of its donation attempts to compare-and-swap races and starved exactly the heavy packets).
+// Tasks are stolen from in the same way.  Results:
+//   counts:  order-free -- tasks and robbed packets atomicAdd into the (zeroed) output;
+//   column densities: a ray's terms must be added in ascending primitive order, i.e. a unit's own
+//     terms first, then the subtrees stolen from it from the LATEST to the first (later thefts
+//     take entries from higher up the stack), recursively.  Packets add their own terms in
+//     registers as always; tasks write theirs to chunk chains; a robbed packet leaves its sum in a
+//     root slot and a second launch ("fold", one warp per root) walks the theft tree depth-first,
+//     one cursor per nesting level on the ordinary traversal stack.  A task that could not get a
+//     chunk (pool exhausted) is marked aborted and its subtree is walked by the fold unit itself,
+//     in place -- slower, never wrong.
+// Hit lists (SUB = false), over several launches: every hit's write position depends on the
+// number of hits before it, so an over-budget unit is suspended once no unclaimed unit is left
+// and resumed as tasks over disjoint subsets of 8, 2, 1 of its RAYS, each with the whole stack
+// and its own cursors.
+constexpr int PK_REC_WORDS = 8 + 2 * PK_STACK + 3 * 32;   // hit lists: header | stack | cum, count, cursor
+// A theft: {packet, ray subset, number of stack entries, - | older theft from the same unit, then the
+// task's results: first chunk of its term chain, latest theft from IT, status 0/1/2 | the entries}
+constexpr int PK_DON_MAX = 32;                      // stack entries per theft: the bottom ones up to the first big subtree
+constexpr int PK_DREC_WORDS = 8 + 2 * PK_DON_MAX;
+enum { PK_DR_PACKET = 0, PK_DR_SUBSET = 1, PK_DR_N = 2, PK_DR_OLDER = 4, PK_DR_HEAD = 5, PK_DR_DONS = 6, PK_DR_STATUS = 7, PK_DR_ENTRIES = 8 };
+#ifndef PK_CHECK_EVERY_V
+#define PK_CHECK_EVERY_V 8
+#endif
+constexpr int PK_CHECK_EVERY = PK_CHECK_EVERY_V;    // steps between looks at the mailbox
+#ifndef PK_DON_MINR_V
+#define PK_DON_MINR_V 64
+#endif
+constexpr int PK_DON_MINR = PK_DON_MINR_V;          // smallest subtree (leaves spanned) worth a task
+constexpr int PK_SAMPLE = 4;                        // 128-byte lines of slot words a thief samples per scan
+constexpr int PK_ADV = 256;                         // notice board: slots of long-running units (hints, may be stale)
+constexpr int PK_ADV_AGE = 256;                     // steps after which a unit puts itself on the board
+constexpr int PK_SPIN_LIMIT = 1 << 20;              // polls (up to ~4 us apart) before a waiting warp gives up (error 3)
+
+enum { PK_KIND_PACKETS = 0, PK_KIND_TASKS = 1, PK_KIND_FOLD = 2 };
+enum { PK_LB_FINISHED = 0, PK_LB_CREATED = 1 };     // units finished; tasks created (= theft records)
+
 struct PkTasks {
-    const int2* tasks_in;     // {record, ray subset}; NULL in round 0 (units are packets)
-    const int* n_tasks_in;
-    int2* tasks_out;          // NULL in the last round (run to completion)
-    int* n_tasks_out;
-    int* records;
-    int* n_records;
+    int kind;
+    int* records;             // theft records (PK_DREC_WORDS) or, hit lists, suspended traversals (PK_REC_WORDS)
+    int* n_records;           // hit lists only
     int tasks_cap, records_cap;
-    int budget;               // steps (inner nodes + leaves) before a unit may be suspended
-    int eager;                // 0: suspend only once every unit of the launch has been claimed
+    int budget;               // steps (inner nodes + leaves) before a unit may be robbed / suspended
+    int eager;                // 1: any subtree is worth a task, suspension at `budget` regardless (tests)
+    // ---- work stealing (counts, column densities) ----
+    int* state; int* resp; int n_slots;       // one word per resident warp, see pk_serve
+    int* adv;                                 // PK_ADV hints
+    int* lb;                       // PK_LB_*
+    char* pool; int* pool_ctr; int pool_cap;
+    int2* roots; float* root_cum; int* n_roots;    // robbed packets: {packet, latest theft}, their own sums
+    // ---- ray-subset rounds (hit lists) ----
+    const int2* tasks_in;     // PK_KIND_TASKS: {record, ray subset}
+    const int* n_tasks_in;
+    int2* tasks_out;          // NULL: run to completion
+    int* n_tasks_out;
     int child_width;          // lanes per child task
-    // Dynamic mode (single launch): suspended traversals go to a queue that idle warps of the SAME
-    // launch drain.  queue[i] = {record, ray subset} stored as one 64-bit word; record -1 = not
-    // published yet.
-    int dynamic;
-    int2* queue; int queue_cap;
-    int* q_head;              // next slot to claim
-    int* q_tail;              // slots reserved so far
-    int* finished;            // packets + tasks finished so far; the launch is over when it equals
-                              // n_packets + q_tail (every reserved slot is published and consumed)
-    // running statistics of the units that completed without being split: a unit is only worth
-    // splitting when it is much heavier than the typical one
+    // running statistics of the units that completed unsplit -- ray-subset tasks lose SIMD width,
+    // so a unit is only split when it is much heavier than the typical one
     unsigned long long* sum_steps;
     int* n_done;
 };
@@ -497,7 +620,6 @@ struct PkTasks {
 #define PK_AVG_FACTOR_X4_V 8
 #endif
 constexpr int PK_AVG_FACTOR_X4 = PK_AVG_FACTOR_X4_V;   // split units heavier than FACTOR/4 x the mean
-constexpr int PK_SPIN_LIMIT = 1 << 20;     // polls (up to ~4 us apart) before an idle warp gives up (error 3)
 
 // Claim `n` consecutive slots of a bounded pool; -1 if they do not fit.
 __device__ __forceinline__ int pk_reserve(int* counter, int n, int cap)
@@ -510,6 +632,14 @@ __device__ __forceinline__ int pk_reserve(int* counter, int n, int cap)
         cur = seen;
     }
 }
+
+#ifdef PK_DEBUG_LB
+__device__ unsigned long long pk_dbg[32];
+__device__ __forceinline__ unsigned long long pk_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define PK_DBG(x) x
+#else
+#define PK_DBG(x)
+#endif
 
 struct PkArgs {
     const grace_b200_ray* rays; int n_packets;
@@ -530,20 +660,166 @@ struct PkArgs {
         }                                                                                \
     } while (0)
 
+// Slot word of a warp: 0 = nothing to steal here, s > 0 = a unit is walking, has run s - 1 steps and
+// holds a stack entry, s < 0 = thief -s - 1 has asked for work.  Only the owner stores to the word
+// (atomicExch at every check and when its unit ends, which also collects a pending request); a thief
+// may only compare-and-swap a positive value it has just read into its request -- so a request can
+// only land on a walking unit, which is certain to collect it.
+//
+// Victim side: thief `thief` asked.  Hand over the bottom of the stack if it holds a subtree worth a
+// task.  Returns the theft record, or -1 (nothing given; stack untouched).  On success *given
+// entries have left and the ones kept have moved down: W.stack[0, sp - *given).
+template <int MODE, int M4>
+__device__ __noinline__ int pk_serve(PkWarp<MODE, M4>& W, const PkTasks& T, const int4* __restrict__ nodes, int n_nodes,
+                                     int thief, int sp, int packet, unsigned subset, int prev_don, int lane, int* given)
+{
+    // The bottom entries up to and including the first one that spans enough leaves to be worth a task
+    // (the tree is not balanced: the entry at the very bottom may be a single leaf with a large
+    // subtree right above it).  They leave together -- taking an entry from the middle would put the
+    // thief's terms in the middle of the victim's own.
+    int rslot = -1, d = 0;
+    const int look = min(sp, PK_DON_MAX);
+    int2 e = make_int2(0, 0);
+    int size = 0;
+    if (lane < look) {
+        e = W.stack[lane];
+        size = 1;
+        if (e.x < n_nodes) { const int4 n0 = __ldg(nodes + 4 * (size_t)e.x); size = n0.w - n0.z + 1; }
+    }
+    const unsigned big = __ballot_sync(0xffffffffu, lane < look && size >= (T.eager ? 1 : PK_DON_MINR));
+    if (big) {
+        d = __ffs(big);           // entries [0, d)
+        if (lane == 0) { rslot = atomicAdd(T.lb + PK_LB_CREATED, 1); if (rslot >= T.records_cap) rslot = -1; }
+        rslot = __shfl_sync(0xffffffffu, rslot, 0);
+    }
+    if (rslot >= 0) {
+        int* rec = T.records + (size_t)rslot * PK_DREC_WORDS;
+        if (lane == 0) {
+            ((int4*)rec)[0] = make_int4(packet, (int)subset, d, 0);
+            ((int4*)rec)[1] = make_int4(prev_don, -1, -1, 0);
+        }
+        if (lane < d) ((int2*)(rec + PK_DR_ENTRIES))[lane] = e;
+        int2 ev[PK_STACK / 32 + 1];      // the entries kept move down by d
+#pragma unroll
+        for (int k = 0; k <= PK_STACK / 32; ++k) {
+            const int i = lane + 32 * k;
+            if (i + d < sp) ev[k] = W.stack[i + d];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k <= PK_STACK / 32; ++k) {
+            const int i = lane + 32 * k;
+            if (i + d < sp) W.stack[i] = ev[k];
+        }
+        __threadfence();          // the record before the answer
+    }
+    __syncwarp();
+    if (lane == 0) *(volatile int*)(T.resp + thief) = rslot >= 0 ? rslot : -2;
+    *given = d;
+    return rslot;
+}
+
+// Thief side (whole warp).  Returns a theft record to run as a task, or -1 when everything is done.
+__device__ __noinline__ int pk_steal(const PkArgs& P, const PkTasks& T, int me, int n_units, int lane)
+{
+    unsigned rng = (unsigned)me * 2654435761u + (unsigned)clock();
+    unsigned backoff = 128, retry = 1024;
+    const int min_age = max(T.budget, 1);
+    PK_DBG(const unsigned long long w0 = pk_now(); if (lane == 0) atomicMin(&pk_dbg[4], w0);)
+    for (int spins = 0;; ++spins) {
+        // ---- scan: the longest-running unit among PK_SAMPLE runs of 32 consecutive slots (one 128-byte
+        // line per load: thousands of thieves looking at random WORDS saturated the L2 and slowed the
+        // walking units more than the stealing helped) ----
+        int best = 0, bv = -1;
+        const int n_lines = T.n_slots >> 5;
+#pragma unroll
+        for (int k = 0; k < PK_SAMPLE; ++k) {
+            rng = rng * 1664525u + 1013904223u;
+            const int v = (int)(((unsigned long long)rng * (unsigned)n_lines) >> 32) * 32 + lane;
+            const int st = __ldcg(T.state + v);
+            if (st > best) { best = st; bv = v; }
+        }
+        // ... and the units on the notice board: near the end of a launch the few units still walking
+        // are the long-running ones, and a random sample of the slots mostly misses them
+#pragma unroll
+        for (int k = 0; k < PK_ADV / 32; ++k) {
+            const int v = __ldcg(T.adv + k * 32 + lane) - 1;
+            if (v >= 0) { const int st = __ldcg(T.state + v); if (st > best) { best = st; bv = v; } }
+        }
+        // every lane now holds the longest-running unit of its dozen candidates; one of the lanes that
+        // found somebody old enough is drawn at random (if all thieves went for THE longest-running
+        // unit they would collide on its slot word, and it answers one request per check)
+        const unsigned cand = __ballot_sync(0xffffffffu, best > min_age);
+        if (cand) {
+            rng = rng * 1664525u + 1013904223u;
+            int pick = (int)(((unsigned long long)rng * (unsigned)__popc(cand)) >> 32);
+            unsigned cm = cand;
+            while (pick-- > 0) cm &= cm - 1;
+            bv = __shfl_sync(0xffffffffu, bv, __ffs(cm) - 1);
+            int got = -3;         // -3: the request could not be posted
+            if (lane == 0) {
+                *(volatile int*)(T.resp + me) = -1;
+                __threadfence();
+                // the word changes at every check of its owner: a few attempts on its current value
+                bool posted = false;
+                for (int tries = 0; tries < 4 && !posted; ++tries) {
+                    const int cur = *(volatile int*)(T.state + bv);
+                    if (cur <= min_age) break;                 // gone, hidden, or somebody else's request is there
+                    posted = atomicCAS(T.state + bv, cur, -(me + 1)) == cur;
+                }
+                if (posted) {
+                    int polls = 0;
+                    for (;;) {
+                        got = *(volatile int*)(T.resp + me);
+                        if (got != -1) break;
+                        if (++polls > PK_SPIN_LIMIT) { atomicMax(P.err_flag, 3); got = -4; break; }
+                        __nanosleep(500);
+                    }
+                }
+            }
+            got = __shfl_sync(0xffffffffu, got, 0);
+            PK_DBG(if (lane == 0) atomicAdd(&pk_dbg[got >= 0 ? 16 : got == -2 ? 17 : 18], 1ull);)
+            if (got >= 0) { __threadfence(); PK_DBG(if (lane == 0) atomicAdd(&pk_dbg[8], pk_now() - w0);) return got; }
+            if (got == -4) return -1;
+            // refused, or the word had moved on: look again, less and less eagerly (walking units answer one
+            // request per check; thousands of thieves must not take their memory bandwidth meanwhile)
+            __nanosleep(retry);
+            if (retry < 32768) retry *= 2;
+            continue;
+        }
+        // ---- nobody worth robbing in the sample: finished?  `finished` and `created` only grow and
+        // finished <= n_units + created always holds, so equality with `created` read AFTER `finished`
+        // proves that no unit is walking and none is on its way ----
+        int done = 0;
+        if (lane == 0) {
+            const int f = *(volatile int*)(T.lb + PK_LB_FINISHED);
+            __threadfence();
+            const int c = *(volatile int*)(T.lb + PK_LB_CREATED);
+            done = f >= n_units + min(c, T.records_cap);
+            if (spins > PK_SPIN_LIMIT) { atomicMax(P.err_flag, 3); done = 1; }
+        }
+        if (__shfl_sync(0xffffffffu, done, 0)) { PK_DBG(if (lane == 0) atomicAdd(&pk_dbg[9], pk_now() - w0);) return -1; }
+        PK_DBG(if (lane == 0) atomicAdd(&pk_dbg[19], 1ull);)
+        __nanosleep(backoff);
+        if (backoff < 4096) backoff *= 2;
+    }
+}
+
 // Seven CTAs per SM (72 registers) for hit counts and column densities: hit counts carry no FIFO
-// and no accumulators and gain 4 % (13.4 -> 12.8 ms); the column-density kernel spills 48 bytes at
-// 72 registers and still gains 1.3 % at 2^20 rays and 4.5 % at 2^17 (the 192-entry stack is what
-// lets the seventh CTA's shared memory fit).  Hit lists (more shared memory) stay at 6.
+// and no accumulators and gain 4 % (13.4 -> 12.8 ms); the column-density kernel still gains 1.3 %
+// at 2^20 rays and 4.5 % at 2^17 despite a few spilled bytes.  Hit lists (more shared memory) stay at 6.
 #ifndef PK_MIN_BLOCKS_LIGHT_V
 #define PK_MIN_BLOCKS_LIGHT_V 7
 #endif
-template <int MODE, int M4, bool PROF, bool WIDE>
-__global__ void __launch_bounds__(PK_THREADS, ((MODE == MODE_COUNT || MODE == MODE_CUMULATIVE) && !PROF && !WIDE)
+template <int MODE, int M4, bool PROF>
+__global__ void __launch_bounds__(PK_THREADS, ((MODE == MODE_COUNT || MODE == MODE_CUMULATIVE) && !PROF)
                                                   ? PK_MIN_BLOCKS_LIGHT_V : PK_MIN_BLOCKS)
-trace_packet_kernel(const PkArgs P, const PkTasks T)
+trace_packet_kernel(const __grid_constant__ PkArgs P, const __grid_constant__ PkTasks T)
 {
     using Warp = PkWarp<MODE, M4>;
     constexpr bool NEED_Q = Warp::NEED_Q;
+    constexpr bool SUB = MODE != MODE_FILL;           // subtree donation; hit lists: ray-subset rounds
+    constexpr bool CHAIN = MODE == MODE_CUMULATIVE;   // ordered term chains + fold
     extern __shared__ __align__(16) unsigned char pk_smem[];
     double2* s_table = (double2*)pk_smem;     // {T[i], T[i+1] - T[i]}
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -555,71 +831,50 @@ trace_packet_kernel(const PkArgs P, const PkTasks T)
         }
         __syncthreads();
     }
+    if (lane == 0) { W.pool = T.pool; W.pool_ctr = T.pool_ctr; W.pool_cap = T.pool_cap; W.ch_on = 0; W.ch_fail = 0; }
     const float4* __restrict__ spheres = P.spheres;
     const int4* __restrict__ nodes = P.nodes;
     const int4* __restrict__ leaves = P.leaves;
     const int n_nodes = P.n_nodes;
     const int root = __ldg(P.root_ptr);
     const unsigned lt = gb_lanemask_lt();
-    const int n_units = T.tasks_in ? min(__ldg(T.n_tasks_in), T.tasks_cap) : P.n_packets;
+    const bool donating = SUB && !PROF && T.kind == PK_KIND_PACKETS && T.state != nullptr;
+    const int n_units = T.kind == PK_KIND_PACKETS ? P.n_packets
+                      : T.kind == PK_KIND_TASKS ? min(__ldg(T.n_tasks_in), T.tasks_cap)
+                                                : __ldg(T.n_roots);
+
+    PK_DBG(if (threadIdx.x == 0 && blockIdx.x == 0) atomicMin(&pk_dbg[7], pk_now());)
+    const int me = blockIdx.x * PK_WARPS + warp;          // this warp's slot (state, mailbox, answer cell)
 
     for (;;) {
         int unit = -1;
-        int2 task = make_int2(-1, 0);
         if (lane == 0) {
-            // volatile pre-check keeps the ticket from running away while idle warps poll
+            // volatile pre-check keeps the ticket from running away
             if (*(volatile int*)P.unit_counter < n_units) unit = atomicAdd(P.unit_counter, 1);
             if (unit >= n_units) unit = -1;
-            if (unit < 0 && T.dynamic) {
-                // every packet has been claimed: drain the queue of suspended traversals
-                int spins = 0;
-                unsigned backoff = 64;
-                for (;;) {
-                    // `finished` is read BEFORE `q_tail`: both only grow, finished <= n_packets + q_tail
-                    // always holds, so equality of the two samples proves that everything is done
-                    const int f = *(volatile int*)T.finished;
-                    const int t = *(volatile int*)T.q_tail;
-                    const int h = *(volatile int*)T.q_head;
-                    if (h < t) {
-                        if (atomicCAS(T.q_head, h, h + 1) != h) continue;
-                        // reserved before published: wait for the publisher's store
-                        int2 e;
-                        int wait = 0;
-                        do {
-                            const unsigned long long v = *(volatile unsigned long long*)(T.queue + h);
-                            e = make_int2((int)(unsigned)v, (int)(unsigned)(v >> 32));
-                        } while (e.x == -1 && ++wait < PK_SPIN_LIMIT);
-                        if (e.x < 0) { atomicMax(P.err_flag, 3); atomicAdd(T.finished, 1); continue; }
-                        task = e;
-                        unit = n_units + h;
-                        break;
-                    }
-                    if (f >= n_units + t) break;
-                    if (++spins > PK_SPIN_LIMIT) { atomicMax(P.err_flag, 3); break; }
-                    __nanosleep(backoff);
-                    if (backoff < 4096) backoff *= 2;
-                }
-            }
         }
         unit = __shfl_sync(0xffffffffu, unit, 0);
-        if (unit < 0) break;
+        int my_task = -1;                 // >= 0: this unit is a stolen subtree (its theft record)
+        if (unit < 0) {
+            if (!donating) break;
+            my_task = pk_steal(P, T, me, n_units, lane);      // every packet has been claimed: rob a walking unit
+            if (my_task < 0) break;
+        }
         int packet = unit;
         unsigned subset = 0xffffffffu;
         const int* rec = nullptr;
-        int level = 0;                    // dynamic mode: how many times this traversal has been split
-        if (T.dynamic && unit >= n_units) {
-            task.x = __shfl_sync(0xffffffffu, task.x, 0);
-            task.y = __shfl_sync(0xffffffffu, task.y, 0);
-            rec = T.records + (size_t)task.x * PK_REC_WORDS;
-            packet = __ldcg(rec + 0);
-            level = __ldcg(rec + 5);
-            subset = (unsigned)task.y;
-        } else if (T.tasks_in) {
+        if (my_task >= 0) {
+            rec = T.records + (size_t)my_task * PK_DREC_WORDS;
+            packet = __ldcg(rec + PK_DR_PACKET);
+            subset = (unsigned)__ldcg(rec + PK_DR_SUBSET);
+        } else if (T.kind == PK_KIND_TASKS) {
             const int2 t = T.tasks_in[unit];
-            if (t.x < 0) continue;            // slot claimed but never filled (pool was full)
+            if (t.x < 0) continue;            // slot claimed but never filled
             rec = T.records + (size_t)t.x * PK_REC_WORDS;
             packet = rec[0];
             subset = (unsigned)t.y;
+        } else if (T.kind == PK_KIND_FOLD) {
+            packet = __ldg(&T.roots[unit].x);
         }
         const bool lane_on = (subset >> lane) & 1u;
         const int ray_index = packet * 32 + lane;
@@ -658,19 +913,26 @@ trace_packet_kernel(const PkArgs P, const PkTasks T)
         A.count = 0; A.cum = 0.0f; A.cursor = 0; A.qn = 0; A.room = PK_QD;
         A.hit_idx = P.hit_idx; A.hit_integral = P.hit_integral; A.hit_dist = P.hit_dist;
         int sp = 0;
-        int top = root;                  // !WIDE: top of stack in a register
+        int top = root;                  // top of stack in a register; -1 = empty, <= -2 = FOLD entry
         unsigned top_mask = 0xffffffffu;
-        if (WIDE && !rec) {              // WIDE: everything lives in the stack, {index, parent link}
-            if (lane == 0) W.stack[0] = make_int2(root, 0);
-            sp = 1;
-        }
-        if (rec) {      // resume a suspended traversal for the rays in `subset`
-            // L1-bypassing loads: in dynamic mode the record was written by another SM during this
-            // launch, and a line cached for a neighbouring record may cover its first words
+        if (CHAIN && lane == 0) { W.ch_on = 0; W.ch_fail = 0; W.ch_cur = -1; W.ch_head = -1; }
+        if (SUB && my_task >= 0) {
+            // stolen stack entries, for all rays of the unit they were taken from
+            sp = __ldcg(rec + PK_DR_N);
+            if (lane < sp) W.stack[lane] = __ldcg((const int2*)(rec + PK_DR_ENTRIES) + lane);
+            if (CHAIN && lane == 0) W.ch_on = 1;
+            __syncwarp();
+            PK_POP();
+        } else if (SUB && T.kind == PK_KIND_FOLD) {
+            // a robbed packet: its own sum, then what was stolen from it, latest theft first.  A fold
+            // cursor is the stack entry {-2 - theft record, all lanes}
+            A.cum = __ldg(T.root_cum + (size_t)unit * 32 + lane);
+            top = -2 - __ldg(&T.roots[unit].y);
+        } else if (rec) {                // hit lists: the whole traversal state, for the rays in `subset`
             sp = __ldcg(rec + 2); top = __ldcg(rec + 3); top_mask = (unsigned)__ldcg(rec + 4) & subset;
             for (int i = lane; i < sp; i += 32) W.stack[i] = __ldcg((const int2*)(rec + 8) + i);
             __syncwarp();
-            if (!WIDE && top_mask == 0u) PK_POP();
+            if (top_mask == 0u) PK_POP();
             A.cum = __int_as_float(__ldcg(rec + 8 + 2 * PK_STACK + lane));
             A.count = __ldcg(rec + 8 + 2 * PK_STACK + 32 + lane);
             A.cursor = __ldcg(rec + 8 + 2 * PK_STACK + 64 + lane);
@@ -684,220 +946,141 @@ trace_packet_kernel(const PkArgs P, const PkTasks T)
         const long long pf_t0 = PROF ? clock64() : 0;
         const int guard0 = 2 * n_nodes + 8;   // a depth-first walk enters each node at most once
         int guard = guard0;
-        bool suspended = false;
+        bool suspended = false, aborted = false;
+        int don_head = -1;                // what has been stolen from this unit (latest theft first)
+        int next_check = T.budget, hold_until = 0;
         for (;;) {
-            // ---- suspend an over-budget traversal and hand its rays to several tasks ----
-            // Splitting costs SIMD width (a task owns fewer rays), so it only pays when warps
-            // would otherwise idle: a unit is suspended once it has run `budget` steps AND the
-            // ticket counter shows that no unclaimed unit is left in this launch.
-            const bool may_split = T.dynamic ? level < 3 : T.tasks_out != nullptr;
-            bool split_now = may_split && guard0 - guard >= T.budget && (WIDE ? sp > 0 : top >= 0);
-            if (split_now && !T.eager) {
-                split_now = *(volatile int*)P.unit_counter >= n_units;
-                if (split_now && T.n_done) {          // ... and this unit is heavier than most
-                    const long long nd = *(volatile int*)T.n_done;
-                    const unsigned long long ss = *(volatile unsigned long long*)T.sum_steps;
-                    if (nd > 0) split_now = 4ll * (guard0 - guard) * nd >= (long long)PK_AVG_FACTOR_X4 * (long long)ss;
-                    else split_now = guard0 - guard >= 8 * T.budget;      // nothing to compare with yet
+            if (CHAIN && W.ch_fail) { aborted = true; break; }      // the chunk pool ran dry
+            // ---- every PK_CHECK_EVERY steps: publish progress, collect and answer a thief's request ----
+            if (donating && guard0 - guard >= next_check) {
+                const int steps = guard0 - guard;
+                next_check = steps + PK_CHECK_EVERY;
+                int old = 0;
+                if (lane == 0) {
+                    old = atomicExch(T.state + me, (sp > 0 && steps >= hold_until) ? steps + 1 : 0);
+                    if (steps >= PK_ADV_AGE) T.adv[me & (PK_ADV - 1)] = me + 1;
+                }
+                old = __shfl_sync(0xffffffffu, old, 0);
+                if (old < 0) {
+                    int given = 0;
+                    const int rslot = pk_serve<MODE, M4>(W, T, nodes, n_nodes, -old - 1, sp, packet, subset, don_head, lane, &given);
+                    PK_DBG(if (lane == 0) atomicAdd(&pk_dbg[rslot >= 0 ? 10 : 11], 1ull);)
+                    if (rslot >= 0) { don_head = rslot; sp -= given; next_check = steps + 2; }       // in demand: look again soon
+                    else hold_until = steps + 8 * PK_CHECK_EVERY;       // nothing worth a task down there: stay out of sight a while
                 }
             }
-            if (split_now) {
-                // rays per child task: 8, 2, 1 by round (one launch per round) or by split level (dynamic)
-                const int child_width = T.dynamic ? (level == 0 ? 8 : level == 1 ? 2 : 1) : T.child_width;
-                const unsigned bmask0 = child_width >= 32 ? 0xffffffffu : ((1u << child_width) - 1u);
-                unsigned blocks = 0;          // bit b: some ray of lane block b belongs to this unit
-                for (int b = 0; b * child_width < 32; ++b)
-                    if (subset & (bmask0 << (b * child_width))) blocks |= 1u << b;
-                const int nchild = __popc(blocks);
-                int rslot = -1, tslot = -1;
-                if (child_width >= 32) {       // handed over whole: the per-ray kernel resumes all its rays
-                    if (lane == 0) rslot = pk_reserve(T.n_records, 1, T.records_cap);
-                    tslot = 0;
-                } else if (nchild > 1 && lane == 0) {
-                    // Reserve with compare-and-swap: a counter must never be visible above its
-                    // final value (an add-then-undo would let another warp claim slots past it).
-                    if (T.dynamic) {
-                        rslot = pk_reserve(T.n_records, 1, T.records_cap);
-                        if (rslot >= 0) {
-                            tslot = pk_reserve(T.q_tail, nchild, T.queue_cap);
-                            if (tslot < 0) rslot = -1;              // queue full: keep running (the record slot is lost)
-
-                        }
-                    } else {
+            // ---- hit lists: suspend an over-budget traversal, resume it as ray-subset tasks ----
+            // Splitting costs SIMD width (a task owns fewer rays), so it only pays when warps would
+            // otherwise idle: a unit is suspended once it has run `budget` steps AND the ticket counter
+            // shows that no unclaimed unit is left AND it is heavier than most.
+            if (!SUB && T.tasks_out != nullptr && guard0 - guard >= T.budget && top >= 0) {
+                bool split_now = true;
+                if (!T.eager) {
+                    split_now = *(volatile int*)P.unit_counter >= n_units;
+                    if (split_now && T.n_done) {
+                        const long long nd = *(volatile int*)T.n_done;
+                        const unsigned long long ss = *(volatile unsigned long long*)T.sum_steps;
+                        if (nd > 0) split_now = 4ll * (guard0 - guard) * nd >= (long long)PK_AVG_FACTOR_X4 * (long long)ss;
+                        else split_now = guard0 - guard >= 8 * T.budget;      // nothing to compare with yet
+                    }
+                }
+                if (split_now) {
+                    // rays per child task 8, 2, 1 by round (one launch per round)
+                    const int child_width = T.child_width;
+                    const unsigned bmask0 = (1u << child_width) - 1u;
+                    unsigned blocks = 0;          // bit b: some ray of lane block b belongs to this unit
+                    for (int b = 0; b * child_width < 32; ++b)
+                        if (subset & (bmask0 << (b * child_width))) blocks |= 1u << b;
+                    const int nchild = __popc(blocks);
+                    int rslot = -1, tslot = -1;
+                    if (nchild > 1 && lane == 0) {
                         tslot = pk_reserve(T.n_tasks_out, nchild, T.tasks_cap);
                         if (tslot >= 0) {
                             rslot = pk_reserve(T.n_records, 1, T.records_cap);
-                            if (rslot < 0) {       // no record: publish nothing in the claimed task slots
+                            if (rslot < 0)         // no record: publish nothing in the claimed task slots
                                 for (int c = 0; c < nchild; ++c) T.tasks_out[tslot + c] = make_int2(-1, 0);
-                            }
                         }
                     }
-                }
-                rslot = __shfl_sync(0xffffffffu, rslot, 0);
-                tslot = __shfl_sync(0xffffffffu, tslot, 0);
-                if (rslot >= 0) {
-                    if (NEED_Q) pk_flush<MODE, M4>(W, A, lane, lt, s_table);
-                    int* r = T.records + (size_t)rslot * PK_REC_WORDS;
-                    if (lane == 0) { r[0] = packet; r[1] = (int)subset; r[2] = sp; r[3] = top; r[4] = (int)top_mask; r[5] = level + 1; }
-                    for (int i = lane; i < sp; i += 32) ((int2*)(r + 8))[i] = W.stack[i];
-                    r[8 + 2 * PK_STACK + lane] = __float_as_int(A.cum);
-                    r[8 + 2 * PK_STACK + 32 + lane] = A.count;
-                    r[8 + 2 * PK_STACK + 64 + lane] = A.cursor;
-                    if (T.dynamic) {          // the record must be visible before the queue slots are
-                        __threadfence();
-                        __syncwarp();
+                    rslot = __shfl_sync(0xffffffffu, rslot, 0);
+                    tslot = __shfl_sync(0xffffffffu, tslot, 0);
+                    if (rslot >= 0) {
+                        if (NEED_Q) pk_flush<MODE, M4>(W, A, lane, lt, s_table);
+                        int* r = T.records + (size_t)rslot * PK_REC_WORDS;
+                        if (lane == 0) { r[0] = packet; r[1] = (int)subset; r[2] = sp; r[3] = top; r[4] = (int)top_mask; r[5] = 0; }
+                        for (int i = lane; i < sp; i += 32) ((int2*)(r + 8))[i] = W.stack[i];
+                        r[8 + 2 * PK_STACK + lane] = __float_as_int(A.cum);
+                        r[8 + 2 * PK_STACK + 32 + lane] = A.count;
+                        r[8 + 2 * PK_STACK + 64 + lane] = A.cursor;
+                        if (lane < nchild) {      // lane c publishes the c-th non-empty block
+                            unsigned bb = blocks;
+                            for (int c = 0; c < lane; ++c) bb &= bb - 1;
+                            const int b = __ffs(bb) - 1;
+                            T.tasks_out[tslot + lane] = make_int2(rslot, (int)(subset & (bmask0 << (b * child_width))));
+                        }
+                        suspended = true;
+                        break;
                     }
-                    if (child_width < 32 && lane < nchild) {      // lane c publishes the c-th non-empty block
-                        unsigned bb = blocks;
-                        for (int c = 0; c < lane; ++c) bb &= bb - 1;
-                        const int b = __ffs(bb) - 1;
-                        const unsigned child = subset & (bmask0 << (b * child_width));
-                        if (T.dynamic)        // one 64-bit store: a consumer sees all of the slot or none of it
-                            *(volatile unsigned long long*)(T.queue + tslot + lane) =
-                                (unsigned long long)(unsigned)rslot | ((unsigned long long)child << 32);
-                        else
-                            T.tasks_out[tslot + lane] = make_int2(rslot, (int)child);
-                    }
-                    if (T.dynamic && lane == 0) atomicAdd(T.finished, 1);       // this unit is done as a unit
-                    suspended = true;
-                    break;
                 }
+            }
+            // ---- fold unit: the next pending item is a theft record ----
+            if (CHAIN && top <= -2) {
+                pk_flush<MODE, M4>(W, A, lane, lt, s_table);      // hits of subtrees walked in place come first
+                const int4* drec = (const int4*)(T.records + (size_t)(-2 - top) * PK_DREC_WORDS);
+                const int4 d0 = __ldcg(drec), d1 = __ldcg(drec + 1);      // packet, subset, entries, - | older, head, thefts, status
+                if (sp + 1 + PK_DON_MAX > PK_STACK) { if (lane == 0) atomicMax(P.err_flag, 1); top = -1; sp = 0; continue; }
+                // after this task and everything stolen from it: the previous theft from the same unit
+                if (d1.x >= 0) { if (lane == 0) W.stack[sp] = make_int2(-2 - d1.x, -1); ++sp; }
+                if (d1.w == 1) {
+                    A.cum = pk_fold_chain(T.pool, d1.y, A.cum, lane);
+                    if (d1.z >= 0) { if (lane == 0) W.stack[sp] = make_int2(-2 - d1.z, -1); ++sp; }
+                } else {                      // aborted or never run: walk its subtree here, in place (what was
+                                              // stolen from it before it aborted is covered by that walk and ignored)
+                    if (lane < d0.z) W.stack[sp + lane] = __ldcg((const int2*)((const int*)drec + PK_DR_ENTRIES) + lane);
+                    sp += d0.z;
+                }
+                __syncwarp();
+                PK_POP();
+                continue;
             }
             // ---- phase A: find the next leaves (at most PK_BATCH, in ascending order) ----
             int nb = 0;
             int b_leaf = 0;               // lane b holds batch entry b
             unsigned b_mask = 0;
-            if (WIDE) {
-                // The stack holds the pending subtrees in order, leftmost on top.  While the top is an
-                // inner node, up to 32 entries are popped -- one per lane -- every lane fetches ITS node
-                // and tests both child boxes against the packet bound (one conservative test per box
-                // instead of 32 slab tests), and the surviving children go back in the same order.
-                // Leaves pass through; the run of leaves on top is the next batch.  Which leaves are
-                // visited does not affect results: the per-ray slab test on the leaf's own box (below)
-                // and sphere_test decide.
-                int2 e = make_int2(0, 0);
-                for (;;) {
-                    if (sp == 0) break;
-                    if (--guard < 0) { if (lane == 0) atomicMax(P.err_flag, 2); sp = 0; break; }
-                    const int look = min(sp, PK_BATCH);
-                    e = make_int2(0, 0);
-                    if (lane < look) e = W.stack[sp - 1 - lane];
-                    const unsigned leafm = __ballot_sync(0xffffffffu, lane < look && e.x >= n_nodes);
-                    nb = __ffs(~leafm) - 1;
-                    if (nb > 0) break;
-                    // A wide step pops the top 32 entries and may add one entry per node it expands.
-                    // Only the first `allowed` inner nodes (from the top) are expanded, the rest pass
-                    // through: the last PK_DFS_RESERVE slots are kept for one-node-at-a-time descent.
-                    const int k = min(sp, 32);
-                    if (sp >= PK_STACK) { if (lane == 0) atomicMax(P.err_flag, 1); sp = 0; break; }
-                    if (lane >= look && lane < k) e = W.stack[sp - 1 - lane];
-                    bool inner = lane < k && e.x < n_nodes;
-                    const unsigned innerm = __ballot_sync(0xffffffffu, inner);
-                    const int allowed = max(PK_STACK - PK_DFS_RESERVE - sp, 1);
-                    inner = inner && (__popc(innerm & lt) < allowed);
-                    bool keepL = false, keepR = false;
-                    int4 n0 = make_int4(0, 0, 0, 0);
-                    if (inner) {
-                        const int4* np = nodes + 4 * (size_t)e.x;
-                        n0 = __ldg(np + 0);
-                        if (B.enabled) {
-                            const int4 n1 = __ldg(np + 1);
-                            const int4 n2 = __ldg(np + 2);
-                            const int4 n3 = __ldg(np + 3);
-                            keepL = packet_may_hit_box(B, __int_as_float(n1.x), __int_as_float(n1.y), __int_as_float(n1.z),
-                                                       __int_as_float(n1.w), __int_as_float(n3.x), __int_as_float(n3.y));
-                            keepR = packet_may_hit_box(B, __int_as_float(n2.x), __int_as_float(n2.y), __int_as_float(n2.z),
-                                                       __int_as_float(n2.w), __int_as_float(n3.z), __int_as_float(n3.w));
-                        }
-                    }
-                    if (PROF) pf_nodes += __popc(__ballot_sync(0xffffffffu, inner));
-                    if (!B.enabled) {     // incoherent rays: the reference rule, any ray's slab test
-                        unsigned im = __ballot_sync(0xffffffffu, inner);
-                        while (im) {
-                            const int i = __ffs(im) - 1;
-                            im &= im - 1;
-                            const int4* np = nodes + 4 * (size_t)__shfl_sync(0xffffffffu, e.x, i);
-                            const int4 n1 = __ldg(np + 1);
-                            const int4 n2 = __ldg(np + 2);
-                            const int4 n3 = __ldg(np + 3);
-                            const bool aL = __any_sync(0xffffffffu, lane_on && pk_slab(S, n1.x, n1.y, n1.z, n1.w, n3.x, n3.y));
-                            const bool aR = __any_sync(0xffffffffu, lane_on && pk_slab(S, n2.x, n2.y, n2.z, n2.w, n3.z, n3.w));
-                            if (lane == i) { keepL = aL; keepR = aR; }
-                        }
-                    }
-                    int2 o0 = make_int2(-1, 0), o1 = make_int2(-1, 0);
-                    if (inner) {
-                        if (keepL) o0 = make_int2(n0.x, 2 * e.x);
-                        if (keepR) { if (keepL) o1 = make_int2(n0.y, 2 * e.x + 1); else o0 = make_int2(n0.y, 2 * e.x + 1); }
-                    } else if (lane < k) {
-                        o0 = e;           // leaves, and inner nodes beyond `allowed`, pass through
-                    }
-                    const int cnt = (o0.x >= 0) + (o1.x >= 0);
-                    int incl = cnt;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                        if (lane >= o) incl += t;
-                    }
-                    const int tot = __shfl_sync(0xffffffffu, incl, 31);
-                    const int off = incl - cnt;
-                    __syncwarp();         // every popped entry has been read
-                    const int sp_new = sp - k + tot;
-                    if (o0.x >= 0) W.stack[sp_new - 1 - off] = o0;
-                    if (o1.x >= 0) W.stack[sp_new - 2 - off] = o1;
-                    sp = sp_new;
-                    __syncwarp();
-                }
-                if (nb > 0) {
-                    sp -= nb;
-                    guard -= nb - 1;
-                    b_leaf = e.x - n_nodes;
-                    // per-ray masks: the slab test on the leaf's own box, read from its parent's record
-                    for (int slot = 0; slot < nb; ++slot) {
-                        const int link = __shfl_sync(0xffffffffu, e.y, slot);
-                        const int4* np = nodes + 4 * (size_t)(link >> 1);
-                        const int4 nxy = __ldg(np + 1 + (link & 1));
-                        const int4 nz = __ldg(np + 3);
-                        const bool hit = lane_on && pk_slab(S, nxy.x, nxy.y, nxy.z, nxy.w, (link & 1) ? nz.z : nz.x,
-                                                            (link & 1) ? nz.w : nz.y);
-                        const unsigned m = __ballot_sync(0xffffffffu, hit);
-                        if (lane == slot) b_mask = m;
-                    }
-                }
-            } else {
-                while (top >= 0 && nb < PK_BATCH) {
-                    if (--guard < 0) { if (lane == 0) atomicMax(P.err_flag, 2); top = -1; break; }
-                    if (top < n_nodes) {
-                        if (PROF) ++pf_nodes;
-                        const int4* np = nodes + 4 * (size_t)top;
-                        const int4 n0 = __ldg(np + 0);
-                        const int4 n1 = __ldg(np + 1);
-                        const int4 n2 = __ldg(np + 2);
-                        const int4 n3 = __ldg(np + 3);
-                        const bool hitL = pk_slab(S, n1.x, n1.y, n1.z, n1.w, n3.x, n3.y);
-                        const bool hitR = pk_slab(S, n2.x, n2.y, n2.z, n2.w, n3.z, n3.w);
-                        // a lane that missed an ancestor's box cannot hit anything below it
-                        const unsigned mL = __ballot_sync(0xffffffffu, hitL) & top_mask;
-                        const unsigned mR = __ballot_sync(0xffffffffu, hitR) & top_mask;
-                        if (mL && mR) {
-                            if (sp >= PK_STACK) { if (lane == 0) atomicMax(P.err_flag, 1); top = -1; sp = 0; continue; }
-                            W.stack[sp++] = make_int2(n0.y, (int)mR);
-                            top = n0.x; top_mask = mL;
-                        } else if (mL) {
-                            top = n0.x; top_mask = mL;
-                        } else if (mR) {
-                            top = n0.y; top_mask = mR;
-                        } else {
-                            PK_POP();
-                        }
+            while (top >= 0 && nb < PK_BATCH) {
+                if (--guard < 0) { if (lane == 0) atomicMax(P.err_flag, 2); top = -1; sp = 0; break; }
+                if (top < n_nodes) {
+                    if (PROF) ++pf_nodes;
+                    const int4* np = nodes + 4 * (size_t)top;
+                    const int4 n0 = __ldg(np + 0);
+                    const int4 n1 = __ldg(np + 1);
+                    const int4 n2 = __ldg(np + 2);
+                    const int4 n3 = __ldg(np + 3);
+                    const bool hitL = pk_slab(S, n1.x, n1.y, n1.z, n1.w, n3.x, n3.y);
+                    const bool hitR = pk_slab(S, n2.x, n2.y, n2.z, n2.w, n3.z, n3.w);
+                    // a lane that missed an ancestor's box cannot hit anything below it
+                    const unsigned mL = __ballot_sync(0xffffffffu, hitL) & top_mask;
+                    const unsigned mR = __ballot_sync(0xffffffffu, hitR) & top_mask;
+                    if (mL && mR) {
+                        if (sp >= PK_STACK) { if (lane == 0) atomicMax(P.err_flag, 1); top = -1; sp = 0; continue; }
+                        W.stack[sp++] = make_int2(n0.y, (int)mR);
+                        top = n0.x; top_mask = mL;
+                    } else if (mL) {
+                        top = n0.x; top_mask = mL;
+                    } else if (mR) {
+                        top = n0.y; top_mask = mR;
                     } else {
-                        if (lane == nb) { b_leaf = top - n_nodes; b_mask = top_mask; }
-                        ++nb;
                         PK_POP();
                     }
+                } else {
+                    if (lane == nb) { b_leaf = top - n_nodes; b_mask = top_mask; }
+                    ++nb;
+                    PK_POP();
                 }
             }
-            if (nb == 0) break;
+            if (nb == 0) {
+                if (CHAIN && top <= -2) continue;
+                break;
+            }
             // ---- phase B: all leaf records in one round trip, then all spheres in one ----
             int2 lf = make_int2(0, 0);
             if (lane < nb && b_mask) lf = __ldg((const int2*)(leaves + b_leaf));
@@ -957,11 +1140,48 @@ trace_packet_kernel(const PkArgs P, const PkTasks T)
             }
         }
         if (suspended) continue;
-        if (NEED_Q) pk_flush<MODE, M4>(W, A, lane, lt, s_table);
-        if (MODE == MODE_COUNT && lane_on) P.out_counts[ray_index] = A.count;
-        if (MODE == MODE_CUMULATIVE && lane_on) P.out_cum[ray_index] = A.cum;
-        if (T.dynamic && lane == 0) atomicAdd(T.finished, 1);
-        if (T.n_done && lane == 0) { atomicAdd(T.sum_steps, (unsigned long long)(guard0 - guard)); atomicAdd(T.n_done, 1); }
+        if (NEED_Q && !aborted) pk_flush<MODE, M4>(W, A, lane, lt, s_table);
+        if (donating) {                      // no longer walking: thieves look elsewhere, a late request gets "nothing"
+            if (lane == 0) {
+                const int old = atomicExch(T.state + me, 0);
+                if (old < 0) *(volatile int*)(T.resp + (-old - 1)) = -2;
+                if (guard0 - guard >= PK_ADV_AGE && T.adv[me & (PK_ADV - 1)] == me + 1) T.adv[me & (PK_ADV - 1)] = 0;
+            }
+        }
+        if (SUB && my_task >= 0) {           // a stolen subtree
+            if (CHAIN) {                     // publish its chain (or its failure) and what was stolen from it
+                if (W.ch_fail) aborted = true;
+                pk_chain_close<MODE, M4>(W, lane);
+                if (lane == 0) {
+                    int* r = T.records + (size_t)my_task * PK_DREC_WORDS;
+                    r[PK_DR_HEAD] = W.ch_head; r[PK_DR_DONS] = don_head; r[PK_DR_STATUS] = aborted ? 2 : 1;
+                }
+            }
+            if (MODE == MODE_COUNT && lane_on && A.count) atomicAdd(P.out_counts + ray_index, A.count);
+        } else if (SUB && don_head >= 0) {   // a robbed packet
+            if (MODE == MODE_COUNT && lane_on) atomicAdd(P.out_counts + ray_index, A.count);   // its tasks add to the same (zeroed) cell
+            if (CHAIN) {                     // its own sum goes to a root slot; the fold launch adds the rest
+                int slot = 0;
+                if (lane == 0) slot = atomicAdd(T.n_roots, 1);
+                slot = __shfl_sync(0xffffffffu, slot, 0);
+                T.root_cum[(size_t)slot * 32 + lane] = A.cum;
+                if (lane == 0) T.roots[slot] = make_int2(packet, don_head);
+            }
+        } else {
+            if (MODE == MODE_COUNT && lane_on) P.out_counts[ray_index] = A.count;
+            if (MODE == MODE_CUMULATIVE && lane_on) P.out_cum[ray_index] = A.cum;
+        }
+        if (donating) {
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) atomicAdd(T.lb + PK_LB_FINISHED, 1);
+            PK_DBG(if (lane == 0) {
+                const unsigned long long st = (unsigned long long)(guard0 - guard);
+                if (my_task >= 0) { atomicAdd(&pk_dbg[0], st); atomicMax(&pk_dbg[1], st); atomicMax(&pk_dbg[6], pk_now()); if (st < 16) atomicAdd(&pk_dbg[14], 1ull); }
+                else { atomicAdd(&pk_dbg[2], st); atomicMax(&pk_dbg[3], st); atomicMax(&pk_dbg[5], pk_now()); }
+            })
+        }
+        if (!SUB && T.n_done && lane == 0) { atomicAdd(T.sum_steps, (unsigned long long)(guard0 - guard)); atomicAdd(T.n_done, 1); }
         if (PROF && lane == 0) {
             atomicAdd(P.prof + 0, pf_nodes); atomicAdd(P.prof + 1, pf_leaves);
             atomicAdd(P.prof + 2, pf_staged); atomicAdd(P.prof + 3, pf_kept);

@@ -42,6 +42,7 @@ extern "C" {
 #define GRACE_B200_ECUDA    2   /* CUDA runtime failure */
 #define GRACE_B200_ERANGE   3   /* size exceeds what the 32-bit reference layout can hold */
 #define GRACE_B200_ENOMEM   4
+#define GRACE_B200_EDEVICE  5   /* device-side traversal failure (stack overflow, malformed tree): outputs incomplete */
 
 /* Delta (key-difference) element types accepted by the tree builder. */
 #define GRACE_B200_DELTA_F32 0
@@ -149,6 +150,26 @@ int grace_b200_albvh_build_aabb(grace_b200_ctx* ctx, const float* d_aabbs8, size
                                 void* d_nodes, void* d_leaves, int* d_root, int* h_n_leaves,
                                 void* stream);
 
+/* The build in stages, as the reference's tree-build profilers time it
+ * (tests/profile_tree_gadget/profile_tree_gadget.cu:113-137, tests/profile_tree/profile_tree.cu:113-133).
+ * replaces: ALBVH::build_leaves + the compaction of ALBVH::remove_empty_leaves
+ *   (cuda/kernels/albvh.cuh:785-846).  d_leaves: int4[n] capacity; on return the first L entries are
+ *   the leaves {first, count, 0, 0}, dense and ordered by primitive range (what remove_if leaves
+ *   behind); entries past L are not written.  L goes to *h_n_leaves (stream synchronised) or, with
+ *   NULL, stays on the device for grace_b200_albvh_last_n_leaves(). */
+int grace_b200_albvh_leaves(grace_b200_ctx* ctx, const void* d_deltas, int delta_type, size_t n,
+                            int max_per_leaf, void* d_leaves, int* h_n_leaves, void* stream);
+/* replaces: ALBVH::build_nodes (cuda/kernels/albvh.cuh:854-940).  d_leaf_deltas: n_leaves + 1 deltas
+ *   between consecutive leaves, shifted by one, sentinels at both ends (what ALBVH::copy_leaf_deltas,
+ *   albvh.cuh:51-74,769-782, extracts); d_nodes: int4[4*(n_leaves-1)].  _aabb: d_aabbs8 as in
+ *   grace_b200_albvh_build_aabb. */
+int grace_b200_albvh_nodes_f4(grace_b200_ctx* ctx, const float* d_spheres4, const void* d_leaves,
+                              size_t n_leaves, const void* d_leaf_deltas, int delta_type,
+                              void* d_nodes, int* d_root, void* stream);
+int grace_b200_albvh_nodes_aabb(grace_b200_ctx* ctx, const float* d_aabbs8, const void* d_leaves,
+                                size_t n_leaves, const void* d_leaf_deltas, int delta_type,
+                                void* d_nodes, int* d_root, void* stream);
+
 /* ---- trace ------------------------------------------------------------------ */
 /* A tree as the trace entry points take it (grace::Tree, cuda/nodes.h:14-58). */
 typedef struct {
@@ -159,41 +180,44 @@ typedef struct {
     int max_per_leaf;
 } grace_b200_tree;
 
-/* Traversal schedule (all four return identical results wherever the reference passes
+/* Traversal schedule (all three return identical results wherever the reference passes
  * its own brute-force test, tests/tree_traversal/tree_traversal.cu:84-121).
  *  PACKET (default): 32 consecutive rays share one traversal as in the reference
  *     (cuda/kernels/bintree_trace.cuh:119-193), with a conservatively padded slab test,
  *     staged leaves and deferred on-hit work; the hit set is exactly the brute-force set.
- *  PACKET_WIDE: the same leaf work, but inner nodes are culled against a conservative bound
- *     of the whole packet, 32 nodes at a time (one per lane), instead of one node per step
- *     with 32 slab tests; per-ray slab tests are made on leaf boxes only.  EXPERIMENTAL: same
- *     results, but its stack-bounded expansion degenerates on very heavy packets (several times
- *     slower than PACKET on clustered data); kept for A/B measurements only.
  *  PER_RAY: every lane walks the tree for its own ray (padded slab test).
  *  PACKET_REF: the reference's schedule and slab arithmetic bit for bit; defines the
  *     traversal counters of grace_b200_trace_stats_f4. */
 #define GRACE_B200_TRACE_PER_RAY    0
 #define GRACE_B200_TRACE_PACKET     1
 #define GRACE_B200_TRACE_PACKET_REF 2
-#define GRACE_B200_TRACE_PACKET_WIDE 3
 int grace_b200_set_trace_mode(grace_b200_ctx* ctx, int mode);
-/* Load balancing of the PACKET schedules: once every packet of a launch has been claimed, a
- * packet still running after `steps` inner-node + leaf visits is suspended and resumed as
- * several tasks over disjoint subsets of its rays, so the tail of heavy packets spreads over the
- * idle SMs (results are unaffected: each ray accumulates in the same order).  0 disables
- * splitting; the default is 1024.  OR-ing GRACE_B200_BUDGET_EAGER into `steps` suspends every
- * packet at `steps` whether or not unclaimed work is left (used by the tests to force splits). */
+/* Load balancing of the PACKET schedule.  Hit counts and column densities: work stealing inside
+ * the launch -- a warp without a packet asks the longest-running unit for the bottom subtree of
+ * its stack and walks it for all rays of that unit (the terms of a ray are still added in
+ * ascending primitive order, so results are unaffected); a unit can be robbed once it has run
+ * `steps` inner-node + leaf visits.  Hit lists: once every packet of a launch has been claimed, a
+ * packet still running after `steps` visits is suspended and resumed as tasks over disjoint
+ * subsets of its rays.  0 disables both; the default is 64.  OR-ing GRACE_B200_BUDGET_EAGER into
+ * `steps` makes any subtree worth stealing and suspends every hit-list unit at `steps` whether or
+ * not unclaimed work is left (used by the tests to force splits). */
 #define GRACE_B200_BUDGET_EAGER (1 << 30)
 int grace_b200_set_trace_budget(grace_b200_ctx* ctx, int steps);
-/* Where suspended traversals are resumed: 0 = in follow-up launches, one per split level (tasks
- * of 8, 2, 1 rays); 1 = inside the same launch, from a queue the idle warps drain. */
-int grace_b200_set_trace_dynamic(grace_b200_ctx* ctx, int on);
-/* How suspended packets continue: 0 = as tasks over subsets of 8, 2, 1 of their rays (packet
- * kernel); 1 = whole, one ray per lane, each lane with its own stack (per-ray kernel). */
-int grace_b200_set_trace_resume(grace_b200_ctx* ctx, int per_ray);
+/* Bytes of workspace for the per-hit terms {W, 1/h^2} that column-density tasks record for the
+ * ordered final sum; 0 (default) sizes it from the ray count (64 KiB per ray, 64 MiB to 2 GiB).
+ * A pool that runs dry costs time, not correctness: the affected subtrees are walked again by the
+ * launch that adds the terms up. */
+int grace_b200_set_trace_pool(grace_b200_ctx* ctx, size_t bytes);
+/* Diagnostic: counters of the last hit-count / column-density call's work stealing:
+ * h_stats8 = {units finished, subtrees stolen (tasks), -, -, -, chunks of the term pool taken,
+ * packets robbed, -}.  Synchronises the stream. */
+int grace_b200_trace_balance_stats(grace_b200_ctx* ctx, int* h_stats8, void* stream);
 /* Device-side error flag of the last trace launch: 0 = none, 1 = traversal stack overflow
  * (the reference asserts on this only under GRACE_DEBUG, bintree_trace.cuh:162-164),
- * 2 = traversal did not terminate within 2*n_nodes steps (malformed tree).
+ * 2 = traversal did not terminate within 2*n_nodes steps (malformed tree).  A non-zero flag means
+ * the outputs of that launch are incomplete.  The trace calls that already synchronise
+ * (grace_b200_trace_hits_count_f4) check it themselves and fail with GRACE_B200_EDEVICE; the
+ * asynchronous ones (hit counts, column densities, hit-list fill) cannot: poll this after them.
  * Synchronises the stream. */
 int grace_b200_device_error(grace_b200_ctx* ctx, int* h_flag, void* stream);
 

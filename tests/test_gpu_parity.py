@@ -188,7 +188,7 @@ def test_tree_tiny_and_errors(gb, orc):
 
 
 # ----------------------------------------------------------------------------- trace
-@pytest.fixture(params=["packet", "packet_wide", "ray", "packet_ref"], autouse=True)
+@pytest.fixture(params=["packet", "ray", "packet_ref"], autouse=True)
 def trace_mode(request, gb):
     """Every test below runs under both traversal schedules."""
     gb.set_trace_mode(request.param)
@@ -266,19 +266,19 @@ def test_hit_lists_and_sort(gb, orc, scene):
     assert np.array_equal(host(integ).view(np.uint32), sg.view(np.uint32))
 
 
-@pytest.mark.parametrize("dynamic", [False, True, "per_ray"])
+@pytest.mark.parametrize("pool", ["auto", "tiny", "none"])
 @pytest.mark.parametrize("budget", [8, 100, 1000])
-def test_packet_splitting_is_exact(gb, orc, scene, budget, dynamic, trace_mode):
-    """Over-budget packets are suspended and resumed as ray-subset tasks; with a tiny
-    budget nearly every packet goes through all four rounds.  Results must not change."""
-    if trace_mode not in ("packet", "packet_wide"):
+def test_packet_splitting_is_exact(gb, orc, scene, budget, pool, trace_mode):
+    """Over-budget units are suspended and their pending subtrees handed to tasks (hit counts,
+    column densities: terms recorded in chunk chains and folded in traversal order) or resumed as
+    ray-subset tasks (hit lists); with a tiny budget nearly every packet goes through every
+    round, nested.  With a tiny or empty term pool most tasks abort and the fold launch walks
+    their subtrees itself.  Results must not change."""
+    if trace_mode != "packet":
         pytest.skip("splitting exists only in the production packet schedule")
     d_s, tree, hs, htree, rays = scene
     gb.set_trace_budget(budget, eager=True)
-    # resumed as ray-subset tasks in follow-up launches, from a queue inside the launch, or whole
-    # with one ray per lane (per-ray kernel)
-    gb.set_trace_dynamic(dynamic is True)
-    gb.set_trace_resume(dynamic == "per_ray")
+    gb.set_trace_pool({"auto": 0, "tiny": 20 * 16384, "none": 1}[pool])
     try:
         d_rays = dev(rays)
         cnt = torch.empty(len(rays), dtype=torch.int32, device="cuda")
@@ -298,8 +298,23 @@ def test_packet_splitting_is_exact(gb, orc, scene, budget, dynamic, trace_mode):
         assert np.array_equal(host(dist).view(np.uint32), rdist.view(np.uint32))
     finally:
         gb.set_trace_budget(1024)
-        gb.set_trace_dynamic(False)
-        gb.set_trace_resume(False)
+        gb.set_trace_pool(0)
+
+
+def test_default_splitting_small_launches(gb, orc, scene):
+    """The default policy on launches far smaller than the grid (every packet is suspended at the
+    budget and its subtrees spread over the idle warps): results still exact."""
+    d_s, tree, hs, htree, rays = scene
+    for n in (64, 256, 4096):
+        sub = np.ascontiguousarray(rays[:n])
+        cnt = torch.empty(n, dtype=torch.int32, device="cuda")
+        cum = torch.empty(n, dtype=torch.float32, device="cuda")
+        gb.trace_hitcounts_sph(dev(sub), d_s, tree, cnt)
+        gb.trace_cumulative_sph(dev(sub), d_s, tree, cum)
+        assert gb.device_error() == 0
+        assert np.array_equal(host(cnt), orc.trace_hitcounts(sub, hs, htree))
+        ref = orc.trace_cumulative(sub, hs, htree)
+        assert np.array_equal(host(cum).view(np.uint32), ref.view(np.uint32))
 
 
 def test_axis_aligned_and_degenerate_directions(gb, orc, scene):
