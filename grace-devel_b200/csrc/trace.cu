@@ -443,8 +443,8 @@ int launch_packet(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, int n_packe
     constexpr bool SUB = KMODE != MODE_FILL;          // subtree donation inside the launch (counts, column densities)
     constexpr bool CHAIN = KMODE == MODE_CUMULATIVE;  // ordered term chains + fold launch
     // the per-packet profile counters exist only in a separate MODE_COUNT instantiation
-    auto kernel = (KMODE == MODE_COUNT && d_prof) ? trace_packet_kernel<KMODE, M4, KMODE == MODE_COUNT>
-                                                  : trace_packet_kernel<KMODE, M4, false>;
+    auto kernel = (KMODE == MODE_COUNT && d_prof) ? trace_packet_kernel<KMODE, M4, KMODE == MODE_COUNT, false>
+                                                  : trace_packet_kernel<KMODE, M4, false, false>;
     constexpr size_t psmem = packet_smem_bytes<KMODE, M4>();
     GB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
     int per_sm = 0;
@@ -526,10 +526,12 @@ int launch_packet(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, int n_packe
         kernel<<<full_grid, PK_THREADS, psmem, st>>>(P, T);
         GB_LAUNCH_CHECK();
         if (CHAIN) {
+            auto fold = trace_packet_kernel<KMODE, M4, false, CHAIN>;
+            GB_CUDA(cudaFuncSetAttribute(fold, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
             T.kind = PK_KIND_FOLD;
             T.state = nullptr;
             GB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
-            kernel<<<full_grid, PK_THREADS, psmem, st>>>(P, T);
+            fold<<<full_grid, PK_THREADS, psmem, st>>>(P, T);
             GB_LAUNCH_CHECK();
         }
         return GRACE_B200_OK;

@@ -41,6 +41,14 @@
 // hot loops: 18 integer instructions per test iteration).
 #pragma once
 
+#ifdef PK_DEBUG_LB
+__device__ unsigned long long pk_dbg[32];
+__device__ __forceinline__ unsigned long long pk_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define PK_DBG(x) x
+#else
+#define PK_DBG(x)
+#endif
+
 constexpr int PK_THREADS = 128;
 constexpr int PK_WARPS = PK_THREADS / 32;
 #ifndef PK_MIN_BLOCKS_V
@@ -78,19 +86,21 @@ struct PkWarp {
     float2 q2[NEED_I ? PK_QD * 32 : 2];        // FIFO {distance, index bits}
     // term chain of a recording task (column densities, stolen subtrees): see pk_chain_append
     int ch_on, ch_cur, ch_head, ch_fail;       // recording?  current / first chunk, pool exhausted
-    int ch_off;                                // bytes used in the current chunk
+    int ch_off, ch_nb;                         // bytes and blocks used in the current chunk
     char* pool; int* pool_ctr; int pool_cap;
 };
 
-// Term chains.  A chunk is PK_CH_BYTES: a 32-byte header {int next; int bytes used; ...} followed
-// by blocks, one per FIFO flush: 32 count bytes (terms of lane 0..31) and then the terms {W, 1/h^2},
-// lane after lane, each lane's in emission (= ascending primitive) order.  Nothing is padded: a
-// task in which three of the 32 rays hit anything stores three rays' worth (a [row][lane] layout
-// took 6x the space on incoherent packets and a proportionally longer fold).  Chunks come from a
-// pool by atomic ticket.
+// Term chains.  A chunk is PK_CH_BYTES: a 32-byte header {int next; int blocks; ...}, a directory
+// of PK_CH_NB block descriptors {lane mask, rows | start << 8} and the terms.  One block per FIFO
+// flush: `rows` rows of one {W, 1/h^2} per ACTIVE lane (a lane with at least one term in this
+// flush), lanes with fewer terms padded with {0, 0} -- fma(0, 0, x) = x -- so a term's address needs
+// no prefix sum, and a task in which three of the 32 rays hit anything stores three columns (a
+// fixed [row][32 lanes] layout took 6x the space on incoherent packets).  Each lane's terms are in
+// emission (= ascending primitive) order.  The directory lets the fold know every address of a
+// chunk after ONE dependent load.  Chunks come from a pool by atomic ticket.
 constexpr int PK_CH_BYTES = 16384;
-constexpr int PK_CH_HDR = 32;
-
+constexpr int PK_CH_NB = 64;
+constexpr int PK_CH_TERMS = 32 + 8 * PK_CH_NB;     // byte offset of the first term
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 {
@@ -158,43 +168,42 @@ __device__ __forceinline__ void pk_flush_eval(PkWarp<MODE, M4>& W, int qn, int l
 }
 
 
-// Append the evaluated FIFO cells of all lanes to the unit's term chain as one block.
+// Append the evaluated FIFO cells of all lanes to the unit's term chain as one block.  Out of line:
+// pk_flush_cum is on the hot path of every packet and must not carry this function's registers.
 template <int MODE, int M4>
-__device__ __forceinline__ void pk_chain_append(PkWarp<MODE, M4>& W, int qn, int lane)
+__device__ __noinline__ void pk_chain_append(PkWarp<MODE, M4>& W, int qn, int lane, unsigned lt)
 {
-    int incl = qn;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    const int first = incl - qn;
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    if (total == 0) return;
-    const int size = 32 + 8 * total;
-    int cur = W.ch_cur, off = W.ch_off;
-    if (cur < 0 || off + size > PK_CH_BYTES) {
+    const unsigned mask = __ballot_sync(0xffffffffu, qn > 0);
+    if (mask == 0u) return;
+    const int rows = __reduce_max_sync(0xffffffffu, qn);
+    const int ncols = __popc(mask), rank = __popc(mask & lt);
+    const int size = 8 * rows * ncols;
+    int cur = W.ch_cur, off = W.ch_off, nb = W.ch_nb;
+    if (cur < 0 || nb == PK_CH_NB || off + size > PK_CH_BYTES) {
         if (W.ch_fail) return;                   // pool exhausted earlier: the unit is about to abort
         int id = -1;
         if (lane == 0) { id = atomicAdd(W.pool_ctr, 1); if (id >= W.pool_cap) id = -1; }
         id = __shfl_sync(0xffffffffu, id, 0);
         if (id < 0) { if (lane == 0) W.ch_fail = 1; __syncwarp(); return; }
         if (lane == 0) {
-            if (cur >= 0) *(int2*)(W.pool + (size_t)cur * PK_CH_BYTES) = make_int2(id, off);      // close and link
+            if (cur >= 0) *(int2*)(W.pool + (size_t)cur * PK_CH_BYTES) = make_int2(id, nb);      // close and link
             else W.ch_head = id;
             W.ch_cur = id;
         }
         cur = id;
-        off = PK_CH_HDR;
+        off = PK_CH_TERMS;
+        nb = 0;
     }
-    char* blk = W.pool + (size_t)cur * PK_CH_BYTES + off;
-    ((unsigned char*)blk)[lane] = (unsigned char)qn;
-    float2* t = (float2*)(blk + 32) + first;
+    char* ch = W.pool + (size_t)cur * PK_CH_BYTES;
+    if (lane == 0) ((int2*)(ch + 32))[nb] = make_int2((int)mask, rows | (off << 8));
+    if (qn > 0) {
+        float2* t = (float2*)(ch + off) + rank;
 #pragma unroll
-    for (int j = 0; j < PK_QD; ++j)
-        if (j < qn) t[j] = W.q[j * 32 + lane];
+        for (int j = 0; j < PK_QD; ++j)
+            if (j < rows) t[j * ncols] = j < qn ? W.q[j * 32 + lane] : make_float2(0.f, 0.f);
+    }
     __syncwarp();
-    if (lane == 0) W.ch_off = off + size;
+    if (lane == 0) { W.ch_off = off + size; W.ch_nb = nb + 1; }
 }
 
 // Write the header of the last chunk (the unit is finished).
@@ -203,41 +212,63 @@ __device__ __forceinline__ void pk_chain_close(PkWarp<MODE, M4>& W, int lane)
 {
     __syncwarp();
     const int cur = W.ch_cur;
-    if (cur >= 0 && lane == 0) *(int2*)(W.pool + (size_t)cur * PK_CH_BYTES) = make_int2(-1, W.ch_off);
+    if (cur >= 0 && lane == 0) *(int2*)(W.pool + (size_t)cur * PK_CH_BYTES) = make_int2(-1, W.ch_nb);
 }
 
 // Fold a finished chain into `cum`: each lane adds ITS terms in the order they were emitted,
 // one FFMA per term -- the arithmetic of pk_flush_cum, hence of the unsplit traversal.  Latency
-// is what matters here (a heavy ray's chain is walked by one warp): the next chunk is prefetched
-// into L2 as soon as its id is known, and a block's terms are requested together.
-__device__ __noinline__ float pk_fold_chain(const char* pool, int head, float cum, int lane)
+// is what matters here (a heavy ray's chain is walked by one warp): one dependent load per chunk
+// (header + directory), the next chunk prefetched into L2 as soon as its id is known, and the
+// terms of block b + 1 requested before those of block b are added.  The chains were written by
+// an earlier launch, so the read-only path may cache them.
+__device__ __forceinline__ void pk_fold_load(const char* ch, int2 d, int lane, unsigned lt, float2 (&e)[PK_QD], int& rows)
 {
-    for (int c = head; c >= 0;) {
-        const char* ch = pool + (size_t)c * PK_CH_BYTES;
-        const int2 h = __ldcg((const int2*)ch);          // next, bytes used
+    const unsigned mask = (unsigned)d.x;
+    rows = ((mask >> lane) & 1u) ? (d.y & 0xff) : 0;
+    const int ncols = __popc(mask);
+    const float2* t = (const float2*)(ch + (d.y >> 8)) + __popc(mask & lt);
+#pragma unroll
+    for (int j = 0; j < PK_QD; ++j) if (j < rows) e[j] = __ldg(t + j * ncols);
+}
+
+constexpr int PK_FOLD_G = 8;      // blocks whose terms are requested together (the fold launch's kernel may use 255 registers)
+__device__ __noinline__ float pk_fold_chain(const char* pool, int head, float cum, int lane, unsigned lt)
+{
+    if (head < 0) return cum;
+    const char* ch = pool + (size_t)head * PK_CH_BYTES;
+    int2 h = __ldg((const int2*)ch);             // next, blocks
+    int2 d0 = __ldg((const int2*)(ch + 32) + lane), d1 = __ldg((const int2*)(ch + 32) + 32 + lane);
+    for (;;) {
+        // the next chunk's header and directory are requested now, its terms prefetched into L2
+        int2 nh = make_int2(-1, 0), nd0 = make_int2(0, 0), nd1 = make_int2(0, 0);
+        const char* nch = nullptr;
         if (h.x >= 0) {
-            const char* np = pool + (size_t)h.x * PK_CH_BYTES + lane * 128;
+            nch = pool + (size_t)h.x * PK_CH_BYTES;
+            nh = __ldg((const int2*)nch);
+            nd0 = __ldg((const int2*)(nch + 32) + lane);
+            nd1 = __ldg((const int2*)(nch + 32) + 32 + lane);
 #pragma unroll
-            for (int k = 0; k < PK_CH_BYTES / 4096; ++k) asm volatile("prefetch.global.L2 [%0];" :: "l"(np + k * 4096));
+            for (int k = 0; k < PK_CH_BYTES / 4096; ++k) asm volatile("prefetch.global.L2 [%0];" :: "l"(nch + lane * 128 + k * 4096));
         }
-        int off = PK_CH_HDR;
-        while (off < h.y) {
-            const int n = __ldcg((const unsigned char*)(ch + off) + lane);
-            int incl = n;
+        const int nb = h.y;
+        PK_DBG(if (lane == 0) { atomicAdd(&pk_dbg[20], 1ull); atomicAdd(&pk_dbg[21], (unsigned long long)nb); })
+        for (int b0 = 0; b0 < nb; b0 += PK_FOLD_G) {
+            const int2 dd = b0 < 32 ? d0 : d1;       // a group of 8 lies in one half of the directory
+            float2 e[PK_FOLD_G][PK_QD];
+            int rows[PK_FOLD_G];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
+            for (int g = 0; g < PK_FOLD_G; ++g) {
+                const int2 d = make_int2(__shfl_sync(0xffffffffu, dd.x, (b0 + g) & 31), __shfl_sync(0xffffffffu, dd.y, (b0 + g) & 31));
+                rows[g] = 0;
+                if (b0 + g < nb) pk_fold_load(ch, d, lane, lt, e[g], rows[g]);
             }
-            const float2* t = (const float2*)(ch + off + 32) + (incl - n);
-            float2 e[PK_QD];
 #pragma unroll
-            for (int j = 0; j < PK_QD; ++j) if (j < n) e[j] = __ldcg(t + j);
+            for (int g = 0; g < PK_FOLD_G; ++g)
 #pragma unroll
-            for (int j = 0; j < PK_QD; ++j) if (j < n) cum = __fmaf_rn(e[j].x, e[j].y, cum);
-            off += 32 + 8 * __shfl_sync(0xffffffffu, incl, 31);
+                for (int j = 0; j < PK_QD; ++j) if (j < rows[g]) cum = __fmaf_rn(e[g][j].x, e[g][j].y, cum);
         }
-        c = h.x;
+        if (h.x < 0) break;
+        ch = nch; h = nh; d0 = nd0; d1 = nd1;
     }
     return cum;
 }
@@ -247,7 +278,7 @@ __device__ __noinline__ float pk_flush_cum(PkWarp<MODE, M4>& W, int qn, float cu
 {
     pk_flush_eval<MODE, M4>(W, qn, lane, lt, table);
     if (W.ch_on) {            // recording task: the terms go to the chain, the fold launch adds them
-        pk_chain_append<MODE, M4>(W, qn, lane);
+        pk_chain_append<MODE, M4>(W, qn, lane, lt);
         __syncwarp();
         return cum;
     }
@@ -633,13 +664,6 @@ __device__ __forceinline__ int pk_reserve(int* counter, int n, int cap)
     }
 }
 
-#ifdef PK_DEBUG_LB
-__device__ unsigned long long pk_dbg[32];
-__device__ __forceinline__ unsigned long long pk_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-#define PK_DBG(x) x
-#else
-#define PK_DBG(x)
-#endif
 
 struct PkArgs {
     const grace_b200_ray* rays; int n_packets;
@@ -667,11 +691,11 @@ struct PkArgs {
 // only land on a walking unit, which is certain to collect it.
 //
 // Victim side: thief `thief` asked.  Hand over the bottom of the stack if it holds a subtree worth a
-// task.  Returns the theft record, or -1 (nothing given; stack untouched).  On success *given
-// entries have left and the ones kept have moved down: W.stack[0, sp - *given).
+// task.  Returns record << 6 | entries given, or -1 (nothing given; stack untouched).  On success
+// the entries kept have moved down: W.stack[0, sp - given).
 template <int MODE, int M4>
 __device__ __noinline__ int pk_serve(PkWarp<MODE, M4>& W, const PkTasks& T, const int4* __restrict__ nodes, int n_nodes,
-                                     int thief, int sp, int packet, unsigned subset, int prev_don, int lane, int* given)
+                                     int thief, int sp, int packet, unsigned subset, int prev_don, int lane)
 {
     // The bottom entries up to and including the first one that spans enough leaves to be worth a task
     // (the tree is not balanced: the entry at the very bottom may be a single leaf with a large
@@ -715,8 +739,7 @@ __device__ __noinline__ int pk_serve(PkWarp<MODE, M4>& W, const PkTasks& T, cons
     }
     __syncwarp();
     if (lane == 0) *(volatile int*)(T.resp + thief) = rslot >= 0 ? rslot : -2;
-    *given = d;
-    return rslot;
+    return rslot >= 0 ? (rslot << 6) | d : -1;        // record and number of entries given (<= 32), packed
 }
 
 // Thief side (whole warp).  Returns a theft record to run as a task, or -1 when everything is done.
@@ -811,8 +834,10 @@ __device__ __noinline__ int pk_steal(const PkArgs& P, const PkTasks& T, int me, 
 #ifndef PK_MIN_BLOCKS_LIGHT_V
 #define PK_MIN_BLOCKS_LIGHT_V 7
 #endif
-template <int MODE, int M4, bool PROF>
-__global__ void __launch_bounds__(PK_THREADS, ((MODE == MODE_COUNT || MODE == MODE_CUMULATIVE) && !PROF)
+// FOLD: the instantiation the fold launch runs (column densities only); the packet launch's own
+// instantiation carries none of the fold code.
+template <int MODE, int M4, bool PROF, bool FOLD>
+__global__ void __launch_bounds__(PK_THREADS, FOLD ? 2 : ((MODE == MODE_COUNT || MODE == MODE_CUMULATIVE) && !PROF)
                                                   ? PK_MIN_BLOCKS_LIGHT_V : PK_MIN_BLOCKS)
 trace_packet_kernel(const __grid_constant__ PkArgs P, const __grid_constant__ PkTasks T)
 {
@@ -838,10 +863,9 @@ trace_packet_kernel(const __grid_constant__ PkArgs P, const __grid_constant__ Pk
     const int n_nodes = P.n_nodes;
     const int root = __ldg(P.root_ptr);
     const unsigned lt = gb_lanemask_lt();
-    const bool donating = SUB && !PROF && T.kind == PK_KIND_PACKETS && T.state != nullptr;
-    const int n_units = T.kind == PK_KIND_PACKETS ? P.n_packets
-                      : T.kind == PK_KIND_TASKS ? min(__ldg(T.n_tasks_in), T.tasks_cap)
-                                                : __ldg(T.n_roots);
+    const bool donating = SUB && !PROF && !FOLD && T.kind == PK_KIND_PACKETS && T.state != nullptr;
+    const int n_units = FOLD ? __ldg(T.n_roots)
+                      : T.kind == PK_KIND_TASKS ? min(__ldg(T.n_tasks_in), T.tasks_cap) : P.n_packets;
 
     PK_DBG(if (threadIdx.x == 0 && blockIdx.x == 0) atomicMin(&pk_dbg[7], pk_now());)
     const int me = blockIdx.x * PK_WARPS + warp;          // this warp's slot (state, mailbox, answer cell)
@@ -873,7 +897,7 @@ trace_packet_kernel(const __grid_constant__ PkArgs P, const __grid_constant__ Pk
             rec = T.records + (size_t)t.x * PK_REC_WORDS;
             packet = rec[0];
             subset = (unsigned)t.y;
-        } else if (T.kind == PK_KIND_FOLD) {
+        } else if (FOLD) {
             packet = __ldg(&T.roots[unit].x);
         }
         const bool lane_on = (subset >> lane) & 1u;
@@ -923,7 +947,7 @@ trace_packet_kernel(const __grid_constant__ PkArgs P, const __grid_constant__ Pk
             if (CHAIN && lane == 0) W.ch_on = 1;
             __syncwarp();
             PK_POP();
-        } else if (SUB && T.kind == PK_KIND_FOLD) {
+        } else if (FOLD) {
             // a robbed packet: its own sum, then what was stolen from it, latest theft first.  A fold
             // cursor is the stack entry {-2 - theft record, all lanes}
             A.cum = __ldg(T.root_cum + (size_t)unit * 32 + lane);
@@ -949,6 +973,7 @@ trace_packet_kernel(const __grid_constant__ PkArgs P, const __grid_constant__ Pk
         bool suspended = false, aborted = false;
         int don_head = -1;                // what has been stolen from this unit (latest theft first)
         int next_check = T.budget, hold_until = 0;
+        PK_DBG(unsigned long long dbg_recs = 0; const unsigned long long dbg_t0 = pk_now();)
         for (;;) {
             if (CHAIN && W.ch_fail) { aborted = true; break; }      // the chunk pool ran dry
             // ---- every PK_CHECK_EVERY steps: publish progress, collect and answer a thief's request ----
@@ -962,8 +987,8 @@ trace_packet_kernel(const __grid_constant__ PkArgs P, const __grid_constant__ Pk
                 }
                 old = __shfl_sync(0xffffffffu, old, 0);
                 if (old < 0) {
-                    int given = 0;
-                    const int rslot = pk_serve<MODE, M4>(W, T, nodes, n_nodes, -old - 1, sp, packet, subset, don_head, lane, &given);
+                    const int gave = pk_serve<MODE, M4>(W, T, nodes, n_nodes, -old - 1, sp, packet, subset, don_head, lane);
+                    const int rslot = gave >= 0 ? gave >> 6 : -1, given = gave & 63;
                     PK_DBG(if (lane == 0) atomicAdd(&pk_dbg[rslot >= 0 ? 10 : 11], 1ull);)
                     if (rslot >= 0) { don_head = rslot; sp -= given; next_check = steps + 2; }       // in demand: look again soon
                     else hold_until = steps + 8 * PK_CHECK_EVERY;       // nothing worth a task down there: stay out of sight a while
@@ -1023,15 +1048,21 @@ trace_packet_kernel(const __grid_constant__ PkArgs P, const __grid_constant__ Pk
                 }
             }
             // ---- fold unit: the next pending item is a theft record ----
-            if (CHAIN && top <= -2) {
+            if (FOLD && top <= -2) {
+                PK_DBG(++dbg_recs;)
                 pk_flush<MODE, M4>(W, A, lane, lt, s_table);      // hits of subtrees walked in place come first
                 const int4* drec = (const int4*)(T.records + (size_t)(-2 - top) * PK_DREC_WORDS);
                 const int4 d0 = __ldcg(drec), d1 = __ldcg(drec + 1);      // packet, subset, entries, - | older, head, thefts, status
                 if (sp + 1 + PK_DON_MAX > PK_STACK) { if (lane == 0) atomicMax(P.err_flag, 1); top = -1; sp = 0; continue; }
                 // after this task and everything stolen from it: the previous theft from the same unit
-                if (d1.x >= 0) { if (lane == 0) W.stack[sp] = make_int2(-2 - d1.x, -1); ++sp; }
+                if (d1.x >= 0) {
+                    if (lane == 0) { W.stack[sp] = make_int2(-2 - d1.x, -1); asm volatile("prefetch.global.L2 [%0];" :: "l"(T.records + (size_t)d1.x * PK_DREC_WORDS)); }
+                    ++sp;
+                }
                 if (d1.w == 1) {
-                    A.cum = pk_fold_chain(T.pool, d1.y, A.cum, lane);
+                    // what was stolen from the task comes right after its own chain: have that record on its way
+                    if (d1.z >= 0 && lane == 0) asm volatile("prefetch.global.L2 [%0];" :: "l"(T.records + (size_t)d1.z * PK_DREC_WORDS));
+                    A.cum = pk_fold_chain(T.pool, d1.y, A.cum, lane, lt);
                     if (d1.z >= 0) { if (lane == 0) W.stack[sp] = make_int2(-2 - d1.z, -1); ++sp; }
                 } else {                      // aborted or never run: walk its subtree here, in place (what was
                                               // stolen from it before it aborted is covered by that walk and ignored)
@@ -1078,7 +1109,7 @@ trace_packet_kernel(const __grid_constant__ PkArgs P, const __grid_constant__ Pk
                 }
             }
             if (nb == 0) {
-                if (CHAIN && top <= -2) continue;
+                if (FOLD && top <= -2) continue;
                 break;
             }
             // ---- phase B: all leaf records in one round trip, then all spheres in one ----
@@ -1140,6 +1171,7 @@ trace_packet_kernel(const __grid_constant__ PkArgs P, const __grid_constant__ Pk
             }
         }
         if (suspended) continue;
+        PK_DBG(if (FOLD && lane == 0) { atomicAdd(&pk_dbg[22], dbg_recs); atomicMax(&pk_dbg[23], dbg_recs); atomicMax(&pk_dbg[24], pk_now() - dbg_t0); atomicAdd(&pk_dbg[25], pk_now() - dbg_t0); atomicAdd(&pk_dbg[26], (unsigned long long)(guard0 - guard)); })
         if (NEED_Q && !aborted) pk_flush<MODE, M4>(W, A, lane, lt, s_table);
         if (donating) {                      // no longer walking: thieves look elsewhere, a late request gets "nothing"
             if (lane == 0) {

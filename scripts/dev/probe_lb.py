@@ -28,3 +28,6 @@ for lr in [int(a) for a in sys.argv[1].split(",")]:
         print("lr %d %s: %.2f ms | task steps sum %d max %d (n<16 steps: %d) | packet steps sum %d max %d | first thief +%.2f ms, last packet +%.2f ms, last task +%.2f ms | thief time until a task: sum %.1f ms, until exit: sum %.1f ms | served %d, refused by victim %d | thief attempts: got %d, refused %d, CAS lost %d, empty scans %d | %s" % (
             lr, what, a.elapsed_time(b), d[0], d[1], d[14], d[2], d[3], (d[4] - t0) / 1e6, (d[5] - t0) / 1e6, (d[6] - t0) / 1e6 if d[6] else 0,
             d[8] / 1e6, d[9] / 1e6, d[10], d[11], d[16], d[17], d[18], d[19], gb.trace_balance_stats()), flush=True)
+        if what == "cum":
+            print("   fold: chunks %d blocks %d | records visited sum %d max/root %d | root fold time max %.2f ms sum %.1f ms | inline steps %d" % (
+                d[20], d[21], d[22], d[23], d[24] / 1e6, d[25] / 1e6, d[26]), flush=True)
