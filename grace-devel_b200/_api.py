@@ -32,7 +32,7 @@ __all__ = [
     "uniform_random_rays", "uniform_random_rays_single_octant", "one_to_many_rays",
     "plane_parallel_random_rays", "orthographic_projection_rays", "pinhole_camera_rays",
     "healpix_rays", "synth_gadget_spheres", "exclusive_segmented_scan",
-    "weighted_exclusive_segmented_scan", "offsets_to_segments", "read_gadget", "write_gadget", "gadget_info", "context", "lib", "build_tree", "set_trace_mode", "set_trace_budget", "set_trace_pool", "trace_balance_stats", "device_error", "sharded_trace", "tiles_of_rank",
+    "weighted_exclusive_segmented_scan", "offsets_to_segments", "read_gadget", "write_gadget", "gadget_info", "context", "lib", "build_tree", "set_trace_mode", "set_trace_budget", "set_trace_pool", "trace_balance_stats", "device_error", "sharded_trace", "tiles_of_rank", "take_local", "scatter_back",
 ]
 
 _c = ctypes

@@ -617,7 +617,10 @@ constexpr int PK_CHECK_EVERY = PK_CHECK_EVERY_V;    // steps between looks at th
 constexpr int PK_DON_MINR = PK_DON_MINR_V;          // smallest subtree (leaves spanned) worth a task
 constexpr int PK_SAMPLE = 4;                        // 128-byte lines of slot words a thief samples per scan
 constexpr int PK_ADV = 256;                         // notice board: slots of long-running units (hints, may be stale)
-constexpr int PK_ADV_AGE = 256;                     // steps after which a unit puts itself on the board
+#ifndef PK_ADV_AGE_V
+#define PK_ADV_AGE_V 256
+#endif
+constexpr int PK_ADV_AGE = PK_ADV_AGE_V;                     // steps after which a unit puts itself on the board
 constexpr int PK_SPIN_LIMIT = 1 << 20;              // polls (up to ~4 us apart) before a waiting warp gives up (error 3)
 
 enum { PK_KIND_PACKETS = 0, PK_KIND_TASKS = 1, PK_KIND_FOLD = 2 };
@@ -746,7 +749,10 @@ __device__ __noinline__ int pk_serve(PkWarp<MODE, M4>& W, const PkTasks& T, cons
 __device__ __noinline__ int pk_steal(const PkArgs& P, const PkTasks& T, int me, int n_units, int lane)
 {
     unsigned rng = (unsigned)me * 2654435761u + (unsigned)clock();
-    unsigned backoff = 128, retry = 1024;
+#ifndef PK_RETRY0_V
+#define PK_RETRY0_V 1024
+#endif
+    unsigned backoff = 128, retry = PK_RETRY0_V;
     const int min_age = max(T.budget, 1);
     PK_DBG(const unsigned long long w0 = pk_now(); if (lane == 0) atomicMin(&pk_dbg[4], w0);)
     for (int spins = 0;; ++spins) {

@@ -14,6 +14,8 @@ APIs are replaced by their successors, arithmetic is untouched.
      the kernel relied on pre-Volta lock-step execution
   4. sgpu: __shfl_up / shfl.up PTX / __ballot -> *_sync forms
      (external/sgpu/device/intrinsics.cuh:116-222, ctascan.cuh:154, ctasegscan.cuh:58,63)
+
+  patch_ref.py <reference> <scratch copy> [MAX_BLOCKS]
 """
 import os
 import re
@@ -89,4 +91,11 @@ edit("include/grace/external/sgpu/device/ctascan.cuh",
 edit("include/grace/external/sgpu/device/ctasegscan.cuh",
      lambda s: s.replace("__ballot(flag)", "__ballot_sync(0xffffffffu, flag)")
                 .replace("__ballot(0 != delta_shared[tid])", "__ballot_sync(__activemask(), 0 != delta_shared[tid])"))
+# Optional "tuned reference" (BASELINE.md 2b): the shipped grid cap is sized for a 7-SMX Kepler
+# (kernel_config.h:11, MAX_BLOCKS = 112 = 7 x 16); argv[3] replaces it (e.g. 148 SMs x 8 resident
+# 256-thread blocks) so the reference fills a B200.  Nothing else changes.
+if len(sys.argv) > 3:
+    mb = int(sys.argv[3])
+    edit("include/grace/cuda/kernel_config.h",
+         lambda s: re.sub(r"const int MAX_BLOCKS = 112;", "const int MAX_BLOCKS = %d;" % mb, s))
 print("patched copy written to", dst)
