@@ -676,6 +676,8 @@ int grace_b200_albvh_leaves(grace_b200_ctx* ctx, const void* d_deltas, int delta
     else return gb_set_error(GRACE_B200_EINVAL, "unknown delta_type %d", delta_type);
 #undef GB_LEAVES_CASE
     if (rc) return rc;
+    ctx->leaves_stage_n = n;
+    ctx->leaves_stage_delta_type = delta_type;
     if (h_n_leaves) return grace_b200_albvh_last_n_leaves(ctx, h_n_leaves, stream);
     return GRACE_B200_OK;
 }
@@ -684,9 +686,29 @@ static int albvh_nodes_any(grace_b200_ctx* ctx, const float* d_prims, bool from_
                            size_t n_leaves, const void* d_leaf_deltas, int delta_type, void* d_nodes, int* d_root,
                            void* stream)
 {
-    GB_REQUIRE(ctx && d_prims && d_leaves && d_leaf_deltas && d_nodes && d_root, GRACE_B200_EINVAL, "NULL argument");
+    GB_REQUIRE(ctx && d_prims && d_leaves && d_nodes && d_root, GRACE_B200_EINVAL, "NULL argument");
     GB_REQUIRE(n_leaves >= 2 && n_leaves < (1ull << 31) - 1024, GRACE_B200_EINVAL, "a tree needs at least two leaves");
     cudaStream_t st = (cudaStream_t)stream;
+    if (!d_leaf_deltas) {
+        // straight after grace_b200_albvh_leaves: its leaf-level deltas, zeroed arrival flags and leaf
+        // count are still in the workspace / device scalars
+        GB_REQUIRE(ctx->leaves_stage_n > 0 && ctx->leaves_stage_delta_type == delta_type, GRACE_B200_EINVAL,
+                   "d_leaf_deltas is NULL but no grace_b200_albvh_leaves call with this delta type precedes");
+        const size_t n = ctx->leaves_stage_n;
+        ctx->leaves_stage_n = 0;
+        int* d_nl = ctx->d_scalars + GB_SC_NLEAVES;
+#define GB_NODES_CASE(T)                                                                                   \
+        { BuildWs<T> w;                                                                                    \
+          int rc = build_workspace<T>(ctx, n, &w);                                                         \
+          if (rc) return rc;                                                                               \
+          return nodes_stage<T>(ctx, (const float4*)d_prims, from_aabb, n_leaves, (const int4*)d_leaves, d_nl, w.leaf_deltas, \
+                                w.flags, (int4*)d_nodes, d_root, st); }
+        if (delta_type == GRACE_B200_DELTA_F32) GB_NODES_CASE(float)
+        if (delta_type == GRACE_B200_DELTA_U32) GB_NODES_CASE(uint32_t)
+        if (delta_type == GRACE_B200_DELTA_U64) GB_NODES_CASE(uint64_t)
+#undef GB_NODES_CASE
+        return gb_set_error(GRACE_B200_EINVAL, "unknown delta_type %d", delta_type);
+    }
     unsigned* flags = (unsigned*)gb_workspace(ctx, gb_align(n_leaves * sizeof(unsigned)) + 256);
     if (!flags) return GRACE_B200_ENOMEM;
     GB_CUDA(cudaMemsetAsync(flags, 0, n_leaves * sizeof(unsigned), st));

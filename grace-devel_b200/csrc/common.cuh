@@ -18,6 +18,8 @@ struct grace_b200_ctx {
     int* d_scalars = nullptr;  // small persistent device scalars (tickets, counts)
     int* h_pinned = nullptr;   // pinned host mirror for count read-backs
     int last_n_leaves_valid = 0;
+    size_t leaves_stage_n = 0;       // > 0: the workspace still holds the leaf-level deltas of an albvh_leaves call
+    int leaves_stage_delta_type = 0;
     int trace_mode = GRACE_B200_TRACE_PACKET;
     int trace_budget = 64;     // traversal steps before a unit may donate / be suspended (0 = never)
     size_t trace_pool_bytes = 0;    // term pool of the column-density load balancing (0 = sized from the ray count)
@@ -39,6 +41,7 @@ enum {
     GB_SC_CLASS = 40,       // segmented sort class counters (16 ints) + XL total (2 ints, 8-byte aligned)
     GB_SC_LB = 64,          // trace work donation: {finished, tail, head, idle} (one 16-byte load), then
                             // [4] records, [5] chunks taken, [6] root records
+    GB_SC_MINMAX = 80,      // min/max of four components (8 floats) for the host-returning bounds call
     GB_SC_COUNT = 96
 };
 

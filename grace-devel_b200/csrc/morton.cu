@@ -220,6 +220,20 @@ int grace_b200_minmax_f4(grace_b200_ctx* ctx, const float* d_spheres4, size_t n,
     return run_minmax(ctx, d_spheres4, n, d_minmax8, 4, stream);
 }
 
+int grace_b200_minmax_f4_host(grace_b200_ctx* ctx, const float* d_spheres4, size_t n, float* h_minmax8, void* stream)
+{
+    GB_REQUIRE(ctx && h_minmax8, GRACE_B200_EINVAL, "NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    // result through the context's device scalars and pinned mirror: no allocation per call
+    float* d_out = (float*)(ctx->d_scalars + GB_SC_MINMAX);
+    int rc = run_minmax(ctx, d_spheres4, n, d_out, 4, stream);
+    if (rc) return rc;
+    GB_CUDA(cudaMemcpyAsync(ctx->h_pinned + GB_SC_MINMAX, d_out, 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    GB_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < 8; ++i) h_minmax8[i] = ((const float*)(ctx->h_pinned + GB_SC_MINMAX))[i];
+    return GRACE_B200_OK;
+}
+
 int grace_b200_morton_keys30_f4(grace_b200_ctx* ctx, const float* d_spheres4, size_t n,
                                 const float* d_bounds6, uint32_t* d_keys, void* stream)
 {

@@ -100,12 +100,18 @@ GRACE_HOST void ALBVH_sph(const SphereVec& d_spheres, const DeltaVec& d_deltas, 
 {
     int L = 0;
     const auto* dp = detail::raw(d_deltas.data());
-    GRACE_B200_CHECK(grace_b200_albvh_build_f4(detail::context(), detail::f4(detail::raw(d_spheres.data())),
-                                               d_spheres.size(), dp, detail::delta_type(dp), d_tree.max_per_leaf,
-                                               d_tree.nodes.data(), d_tree.leaves.data(), d_tree.root_index_ptr,
-                                               &L, nullptr));
-    d_tree.nodes.resize(4 * (size_t)(L - 1));      // remove_empty_leaves, albvh.cuh:842-845
+    const size_t n = d_spheres.size();
+    if (d_tree.leaves.size() < n) d_tree.leaves.resize(n);
+    // leaves first: their number sizes the node array (remove_empty_leaves, albvh.cuh:842-845), so a Tree
+    // whose storage has not been touched yet never allocates the 4 (N - 1) int4 it was constructed for
+    GRACE_B200_CHECK(grace_b200_albvh_leaves(detail::context(), dp, detail::delta_type(dp), n, d_tree.max_per_leaf,
+                                             d_tree.leaves.data(), &L, nullptr));
+    d_tree.nodes.resize(4 * (size_t)(L - 1));
     d_tree.leaves.resize((size_t)L);
+    // the leaf-level deltas are still in the library's workspace from the leaves stage
+    GRACE_B200_CHECK(grace_b200_albvh_nodes_f4(detail::context(), detail::f4(detail::raw(d_spheres.data())), d_tree.leaves.data(),
+                                               (size_t)L, nullptr, detail::delta_type(dp), d_tree.nodes.data(),
+                                               d_tree.root_index_ptr, nullptr));
 }
 
 } // namespace grace

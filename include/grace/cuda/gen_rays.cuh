@@ -1,6 +1,8 @@
 // grace/cuda/gen_rays.cuh -- ray generators (reference: cuda/gen_rays.cuh:26-399).
 // Each has a raw-pointer and a container form; the container form grows d_rays if needed.
 #pragma once
+#include "grace/cuda/sort.cuh"      // as in the reference (kernels/gen_rays.cuh:8): sort_by_distance comes along
+#include "grace/cuda/util/extrema.cuh"
 #include "grace/device_vector.h"
 #include "grace/ray.h"
 

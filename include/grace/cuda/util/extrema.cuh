@@ -23,12 +23,13 @@ template <> struct vec_traits<float4>  { typedef float  S; enum { N = 4 }; };
 template <> struct vec_traits<double3> { typedef double S; enum { N = 3 }; };
 template <> struct vec_traits<double4> { typedef double S; enum { N = 4 }; };
 
-template <typename V> __host__ __device__ inline typename vec_traits<V>::S comp_of(const V& v, int k)
-{ return k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : comp_w(v); }
+#ifdef __CUDACC__
 __host__ __device__ inline float comp_w(const float3&) { return 0.f; }
 __host__ __device__ inline float comp_w(const float4& v) { return v.w; }
 __host__ __device__ inline double comp_w(const double3&) { return 0.; }
 __host__ __device__ inline double comp_w(const double4& v) { return v.w; }
+template <typename V> __host__ __device__ inline typename vec_traits<V>::S comp_of(const V& v, int k)
+{ return k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : comp_w(v); }
 
 // out[0..4) = component-wise minima, out[4..8) = maxima; one block per 4096 elements folds into
 // `partial`, the last block to finish (ticket) folds the partials.
@@ -91,8 +92,7 @@ inline void minmax8(const V* d_ptr, size_t n, typename vec_traits<V>::S out[8])
     GRACE_CUDA_CHECK(cudaMemcpy(out, d_out, 8 * sizeof(S), cudaMemcpyDeviceToHost));
 }
 
-template <typename V, typename S>
-inline void minmax_any(const V* d_ptr, size_t n, S out[8]) { minmax8(d_ptr, n, out); }
+#endif // __CUDACC__ (element types other than float4 need the header kernel, hence nvcc)
 
 } // namespace detail
 

@@ -17,20 +17,24 @@ template <typename T>
 class device_vector {
 public:
     typedef T value_type;
+    struct lazy_t {};
     device_vector() : ptr_(nullptr), size_(0), cap_(0) {}
+    // n elements whose storage is allocated at the first data() / resize(): grace::Tree is constructed for
+    // N leaves (1 GiB of nodes at 2^24) and shrunk to a twentieth of that by the builder
+    device_vector(size_t n, lazy_t) : ptr_(nullptr), size_(n), cap_(0) {}
     explicit device_vector(size_t n) : ptr_(nullptr), size_(0), cap_(0) { resize(n); }
     device_vector(size_t n, const T& v) : ptr_(nullptr), size_(0), cap_(0) { resize(n, v); }
     device_vector(const std::vector<T>& h) : ptr_(nullptr), size_(0), cap_(0) { *this = h; }
     device_vector(const device_vector& o) : ptr_(nullptr), size_(0), cap_(0)
     {
         resize(o.size_);
-        if (size_) GRACE_CUDA_CHECK(cudaMemcpy(ptr_, o.ptr_, size_ * sizeof(T), cudaMemcpyDeviceToDevice));
+        if (size_ && o.ptr_) GRACE_CUDA_CHECK(cudaMemcpy(ptr_, o.ptr_, size_ * sizeof(T), cudaMemcpyDeviceToDevice));
     }
     device_vector& operator=(const device_vector& o)
     {
         if (this != &o) {
             resize(o.size_);
-            if (size_) GRACE_CUDA_CHECK(cudaMemcpy(ptr_, o.ptr_, size_ * sizeof(T), cudaMemcpyDeviceToDevice));
+            if (size_ && o.ptr_) GRACE_CUDA_CHECK(cudaMemcpy(ptr_, o.ptr_, size_ * sizeof(T), cudaMemcpyDeviceToDevice));
         }
         return *this;
     }
@@ -44,8 +48,8 @@ public:
 
     size_t size() const { return size_; }
     bool empty() const { return size_ == 0; }
-    T* data() { return ptr_; }
-    const T* data() const { return ptr_; }
+    T* data() { materialise(); return ptr_; }
+    const T* data() const { const_cast<device_vector*>(this)->materialise(); return ptr_; }
 
     // Contents are preserved up to min(old, new) elements.
     void resize(size_t n)
@@ -53,7 +57,7 @@ public:
         if (n > cap_) {
             T* p = nullptr;
             GRACE_CUDA_CHECK(cudaMalloc((void**)&p, n * sizeof(T)));
-            if (size_) GRACE_CUDA_CHECK(cudaMemcpy(p, ptr_, size_ * sizeof(T), cudaMemcpyDeviceToDevice));
+            if (size_ && ptr_) GRACE_CUDA_CHECK(cudaMemcpy(p, ptr_, size_ * sizeof(T), cudaMemcpyDeviceToDevice));
             if (ptr_) GRACE_CUDA_CHECK(cudaFree(ptr_));
             ptr_ = p;
             cap_ = n;
@@ -95,6 +99,12 @@ public:
     }
 
 private:
+    void materialise()
+    {
+        if (ptr_ || size_ == 0) return;
+        GRACE_CUDA_CHECK(cudaMalloc((void**)&ptr_, size_ * sizeof(T)));
+        cap_ = size_;
+    }
     T* ptr_;
     size_t size_, cap_;
 };

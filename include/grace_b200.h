@@ -80,6 +80,11 @@ int grace_b200_bounds_f4(grace_b200_ctx* ctx, const float* d_spheres4, size_t n,
 int grace_b200_minmax_f4(grace_b200_ctx* ctx, const float* d_spheres4, size_t n,
                          float* d_minmax8, void* stream);
 
+/* The same, returned to the host (h_minmax8; the stream is synchronised): what the reference's
+ * min_vec3 / max_vec3 / min_max_x hand back (cuda/util/extrema.cuh:189-230,502-513). */
+int grace_b200_minmax_f4_host(grace_b200_ctx* ctx, const float* d_spheres4, size_t n,
+                              float* h_minmax8, void* stream);
+
 /* replaces: morton_keys_sph / morton::morton_keys_kernel
  *   (cuda/build_sph.cuh:19-34, cuda/kernels/morton.cuh:30-55,97-116).
  * key = interleave(trunc(scale*(c - bot))), scale = span/(top-bot), 10 or 21 bits
@@ -162,7 +167,10 @@ int grace_b200_albvh_leaves(grace_b200_ctx* ctx, const void* d_deltas, int delta
 /* replaces: ALBVH::build_nodes (cuda/kernels/albvh.cuh:854-940).  d_leaf_deltas: n_leaves + 1 deltas
  *   between consecutive leaves, shifted by one, sentinels at both ends (what ALBVH::copy_leaf_deltas,
  *   albvh.cuh:51-74,769-782, extracts); d_nodes: int4[4*(n_leaves-1)].  _aabb: d_aabbs8 as in
- *   grace_b200_albvh_build_aabb. */
+ *   grace_b200_albvh_build_aabb.  d_leaf_deltas may be NULL when the call directly follows
+ *   grace_b200_albvh_leaves on the same context (no other grace_b200 call in between): the leaf-level
+ *   deltas that call extracted are still in the workspace.  This is how the one-call build sizes the
+ *   node array from the leaf count instead of from the primitive count. */
 int grace_b200_albvh_nodes_f4(grace_b200_ctx* ctx, const float* d_spheres4, const void* d_leaves,
                               size_t n_leaves, const void* d_leaf_deltas, int delta_type,
                               void* d_nodes, int* d_root, void* stream);
