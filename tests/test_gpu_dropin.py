@@ -59,11 +59,22 @@ def test_integrate_self_check():
     assert rc == 0 and "Normalized volume integral" in out, out[-2000:]
 
 
-@pytest.mark.parametrize("prog", ["morton_key_30bit_key", "morton_key_63bit_key", "morton_key_kernel_30bit_keys",
-                                  "morton_key_kernel_63bit_keys"])
+@pytest.mark.parametrize("prog", ["morton_key_30bit_key", "morton_key_63bit_key"])
 def test_morton_self_checks(prog):
     rc, out = run(prog)
     assert rc == 0 and "PASSED" in out, out[-2000:]
+
+
+@pytest.mark.parametrize("prog", ["morton_key_kernel_30bit_keys", "morton_key_kernel_63bit_keys"])
+def test_morton_kernel_programs_match_the_reference_build(prog):
+    """tests/morton_key_kernel/*.cu pass the box (-1, 1)^3 to morton_keys_sph but their host loops scale
+    by MAX_KEY as if the box had unit size (30bit_keys.cu:49-55 vs cuda/kernels/morton.cuh:107-113), so they
+    report a mismatch against the reference's own implementation as well.  What must hold is that the same
+    source built against this repository behaves exactly like the build against the reference's headers."""
+    rc, out = run(prog, 10000, "true")
+    rc_ref, out_ref = run("ref_" + prog, 10000, "true")
+    assert rc == rc_ref
+    assert out == out_ref
 
 
 def test_hitcounts_runs():
