@@ -26,7 +26,7 @@ __all__ = [
     "Tree", "RaySortType", "Octants", "N_table", "kernel_integral_table",
     "morton_keys_sph", "morton_keys30_sort_sph", "morton_keys63_sort_sph",
     "euclidean_deltas_sph", "surface_area_deltas_sph", "XOR_deltas_sph", "ALBVH_sph",
-    "trace_hitcounts_sph", "trace_cumulative_sph", "trace_stats_sph", "trace_ray_cost_sph", "trace_packet_profile_sph", "trace_sph", "trace_with_sentinels_sph",
+    "trace_hitcounts_sph", "trace_cumulative_sph", "trace_stats_sph", "trace_ray_cost_sph", "trace_packet_profile_sph", "trace_sph", "trace_with_sentinels_sph", "trace_sorted_tiles",
     "sort_by_distance", "sort_by_key", "exclusive_scan",
     "min_vec3", "max_vec3", "min_max_x", "min_vec4", "max_vec4",
     "uniform_random_rays", "uniform_random_rays_single_octant", "one_to_many_rays",
@@ -471,6 +471,54 @@ def trace_with_sentinels_sph(d_rays, d_spheres, d_tree, d_ray_offsets, index_sen
     """cuda/trace_sph.cuh:171-241: every ray segment ends with one sentinel slot."""
     return _trace_lists(d_rays, d_spheres, d_tree, d_ray_offsets,
                         (index_sentinel, integral_sentinel, distance_sentinel))
+
+
+class _DevArray:
+    """A library-owned device buffer as torch sees it (__cuda_array_interface__)."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 3}
+
+
+_TILE_FN = _c.CFUNCTYPE(_c.c_int, _P, _sz, _sz, _P, _c.c_longlong, _P, _P, _P, _P)
+_t_tiles = _sig("grace_b200_trace_sorted_tiles_f4",
+                [_P, _P, _sz, _P, _sz, _TS, _sz, _sz, _TILE_FN, _P, _c.POINTER(_c.c_longlong), _P])
+
+
+def trace_sorted_tiles(d_rays, d_spheres, d_tree, hit_budget, consume, rays_per_tile=0):
+    """Sorted hit lists of a ray set too large for one trace_sph call (BASELINE config 4), streamed in
+    ray tiles: count -> scan -> fill -> sort_by_distance -> consume(first_ray, offsets, indices,
+    integrals, distances) per tile, in library-owned buffers of `hit_budget` hits that are reused for
+    every tile.  The tensors passed to `consume` are views of those buffers, valid only during the
+    call; torch work issued inside it runs on the library's second stream (the current stream of the
+    callback), overlapping the counting traversal of the next tile.  Returns the total number of hits."""
+    failure = []
+
+    def tramp(user, first, n_rays, p_off, n_hits, p_idx, p_int, p_dist, stream):
+        try:
+            with torch.cuda.stream(torch.cuda.ExternalStream(int(stream))):
+                off = torch.as_tensor(_DevArray(p_off, n_rays, "<i4"), device=d_rays.device)
+                if n_hits > 0:
+                    idx = torch.as_tensor(_DevArray(p_idx, n_hits, "<i4"), device=d_rays.device)
+                    integ = torch.as_tensor(_DevArray(p_int, n_hits, "<f4"), device=d_rays.device)
+                    dist = torch.as_tensor(_DevArray(p_dist, n_hits, "<f4"), device=d_rays.device)
+                else:
+                    idx = torch.empty(0, dtype=torch.int32, device=d_rays.device)
+                    integ = dist = torch.empty(0, dtype=torch.float32, device=d_rays.device)
+                consume(int(first), off, idx, integ, dist)
+            return 0
+        except BaseException as e:      # never let an exception cross the C frame
+            failure.append(e)
+            return 7
+
+    cb = _TILE_FN(tramp)
+    total = _c.c_longlong(0)
+    rc = _t_tiles(*_trace_args(d_rays, d_spheres, d_tree), int(hit_budget), int(rays_per_tile), cb, None,
+                  ctypes.byref(total), _stream())
+    if failure:
+        raise failure[0]
+    _check(rc)
+    return total.value
 
 
 def sort_by_distance(d_hit_distances, d_ray_offsets, d_hit_indices, d_hit_data):

@@ -18,6 +18,11 @@ struct grace_b200_ctx {
     int* d_scalars = nullptr;  // small persistent device scalars (tickets, counts)
     int* h_pinned = nullptr;   // pinned host mirror for count read-backs
     int last_n_leaves_valid = 0;
+    // streamed hit lists (hits.cu): helper context + stream for the sort side, reusable tile buffers
+    grace_b200_ctx* aux = nullptr;
+    cudaStream_t aux_stream = nullptr;
+    char* tile_mem = nullptr;
+    size_t tile_bytes = 0;
     size_t leaves_stage_n = 0;       // > 0: the workspace still holds the leaf-level deltas of an albvh_leaves call
     int leaves_stage_delta_type = 0;
     int trace_mode = GRACE_B200_TRACE_PACKET;

@@ -80,6 +80,9 @@ int grace_b200_destroy(grace_b200_ctx* ctx)
     if (!ctx) return GRACE_B200_OK;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    if (ctx->aux) grace_b200_destroy(ctx->aux);
+    if (ctx->tile_mem) cudaFree(ctx->tile_mem);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->d_scalars) cudaFree(ctx->d_scalars);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);

@@ -368,6 +368,35 @@ int grace_b200_exclusive_scan_i32(grace_b200_ctx* ctx, const int* d_in, int* d_o
     return run_scan(ctx, d_in, d_out, n, 0, d_total, (cudaStream_t)stream);
 }
 
+// Pass 1 of trace_sph in two halves, so that a caller can put other work on the GPU between them:
+// enqueue = hit counts + exclusive scan + asynchronous read-back of the total and of the traversal's
+// error flag; finish = wait for them and check.
+static int hits_count_enqueue(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, size_t n_rays, const float* d_spheres4,
+                              size_t n, const grace_b200_tree* tree, int with_sentinels, int* d_ray_offsets, cudaStream_t st)
+{
+    int rc = grace_b200_trace_hitcounts_f4(ctx, d_rays, n_rays, d_spheres4, n, tree, d_ray_offsets, (void*)st);
+    if (rc) return rc;
+    long long* d_total = (long long*)(ctx->d_scalars + GB_SC_TOTAL64);
+    rc = run_scan(ctx, d_ray_offsets, d_ray_offsets, n_rays, with_sentinels ? 1 : 0, d_total, st);
+    if (rc) return rc;
+    GB_CUDA(cudaMemcpyAsync(ctx->h_pinned + GB_SC_TOTAL64, d_total, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    // the traversal's error flag rides on the same synchronisation: counts from a walk that overflowed
+    // its stack or did not terminate are short, and the fill pass would disagree with them
+    GB_CUDA(cudaMemcpyAsync(ctx->h_pinned + GB_SC_ERRFLAG, ctx->d_scalars + GB_SC_ERRFLAG, sizeof(int),
+                            cudaMemcpyDeviceToHost, st));
+    return GRACE_B200_OK;
+}
+
+static int hits_count_finish(grace_b200_ctx* ctx, long long* h_total_hits, cudaStream_t st)
+{
+    GB_CUDA(cudaStreamSynchronize(st));
+    *h_total_hits = *(long long*)(ctx->h_pinned + GB_SC_TOTAL64);
+    GB_REQUIRE(ctx->h_pinned[GB_SC_ERRFLAG] == 0, GRACE_B200_EDEVICE,
+               "device-side traversal error %d (1 = stack overflow, 2 = walk did not terminate): hit counts are incomplete",
+               ctx->h_pinned[GB_SC_ERRFLAG]);
+    return GRACE_B200_OK;
+}
+
 int grace_b200_trace_hits_count_f4(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, size_t n_rays,
                                    const float* d_spheres4, size_t n, const grace_b200_tree* tree,
                                    int with_sentinels, int* d_ray_offsets, long long* h_total_hits,
@@ -376,27 +405,132 @@ int grace_b200_trace_hits_count_f4(grace_b200_ctx* ctx, const grace_b200_ray* d_
     GB_REQUIRE(ctx && (d_ray_offsets || n_rays == 0) && h_total_hits, GRACE_B200_EINVAL, "NULL argument");
     if (n_rays == 0) { *h_total_hits = 0; return GRACE_B200_OK; }
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = grace_b200_trace_hitcounts_f4(ctx, d_rays, n_rays, d_spheres4, n, tree, d_ray_offsets, stream);
+    int rc = hits_count_enqueue(ctx, d_rays, n_rays, d_spheres4, n, tree, with_sentinels, d_ray_offsets, st);
     if (rc) return rc;
-    long long* d_total = (long long*)(ctx->d_scalars + GB_SC_TOTAL64);
-    rc = run_scan(ctx, d_ray_offsets, d_ray_offsets, n_rays, with_sentinels ? 1 : 0, d_total, st);
-    if (rc) return rc;
-    long long* h_total = (long long*)(ctx->h_pinned + GB_SC_TOTAL64);
-    GB_CUDA(cudaMemcpyAsync(h_total, d_total, sizeof(long long), cudaMemcpyDeviceToHost, st));
-    // the traversal's error flag rides on the same synchronisation: counts from a walk that overflowed
-    // its stack or did not terminate are short, and the fill pass would disagree with them
-    GB_CUDA(cudaMemcpyAsync(ctx->h_pinned + GB_SC_ERRFLAG, ctx->d_scalars + GB_SC_ERRFLAG, sizeof(int),
-                            cudaMemcpyDeviceToHost, st));
-    GB_CUDA(cudaStreamSynchronize(st));
-    *h_total_hits = *h_total;
-    GB_REQUIRE(ctx->h_pinned[GB_SC_ERRFLAG] == 0, GRACE_B200_EDEVICE,
-               "device-side traversal error %d (1 = stack overflow, 2 = walk did not terminate): hit counts are incomplete",
-               ctx->h_pinned[GB_SC_ERRFLAG]);
+    if ((rc = hits_count_finish(ctx, h_total_hits, st))) return rc;
     // trace_sph.cuh:117,137: offsets and totals are int in the reference
     GB_REQUIRE(*h_total_hits <= 0x7fffffffLL, GRACE_B200_ERANGE,
                "%lld hits exceed the 32-bit offsets of the reference layout; tile the rays",
                *h_total_hits);
     return GRACE_B200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Sorted hit lists of an arbitrarily large ray set, streamed in ray tiles (a 4096^2
+// projection of 2^24 particles has ~5e10 hits, 600 GB -- the reference's one-call trace_sph cannot
+// hold it, cuda/trace_sph.cuh:117).  Per tile: count -> scan -> fill -> sort_by_distance -> consumer,
+// in buffers sized by a hit budget and reused for every tile; a tile that would exceed the budget is
+// halved.  Two buffer sets and two streams: the sort and the consumer of tile k run (on a helper
+// context's stream) while the counting traversal of tile k + 1 runs on the caller's stream.
+// ---------------------------------------------------------------------------
+struct TileBufs { int* offsets; int* idx; float* integ; float* dist; cudaEvent_t filled, consumed; };
+
+static int tiles_reserve(grace_b200_ctx* ctx, size_t hit_budget, size_t tile_rays)
+{
+    const size_t per_set = gb_align(tile_rays * 4) + 3 * gb_align(hit_budget * 4);
+    if (ctx->tile_bytes >= 2 * per_set && ctx->tile_mem) return GRACE_B200_OK;
+    if (ctx->tile_mem) { GB_CUDA(cudaDeviceSynchronize()); GB_CUDA(cudaFree(ctx->tile_mem)); ctx->tile_mem = nullptr; ctx->tile_bytes = 0; }
+    cudaError_t e = cudaMalloc((void**)&ctx->tile_mem, 2 * per_set);
+    if (e != cudaSuccess) return gb_set_error(GRACE_B200_ENOMEM, "hit-list tile buffers: cudaMalloc(%zu) failed: %s", 2 * per_set, cudaGetErrorString(e));
+    ctx->tile_bytes = 2 * per_set;
+    return GRACE_B200_OK;
+}
+
+int grace_b200_trace_sorted_tiles_f4(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, size_t n_rays,
+                                     const float* d_spheres4, size_t n, const grace_b200_tree* tree,
+                                     size_t hit_budget, size_t rays_per_tile, grace_b200_hits_tile_fn consume,
+                                     void* user, long long* h_total_hits, void* stream)
+{
+    GB_REQUIRE(ctx && (d_rays || n_rays == 0) && d_spheres4 && tree, GRACE_B200_EINVAL, "NULL argument");
+    GB_REQUIRE(n_rays % 32 == 0, GRACE_B200_EINVAL, "Number of rays must be a multiple of the warp size (32).");
+    GB_REQUIRE(hit_budget >= 32 && hit_budget <= 0x7fffffffull, GRACE_B200_EINVAL, "hit budget must be in [32, 2^31)");
+    if (h_total_hits) *h_total_hits = 0;
+    if (n_rays == 0) return GRACE_B200_OK;
+    cudaStream_t sa = (cudaStream_t)stream;
+    size_t tile = rays_per_tile ? (rays_per_tile + 31) / 32 * 32 : 65536;
+    if (tile > n_rays) tile = n_rays;
+    // helper context + stream for the sort / consumer side (a context serves one stream at a time)
+    if (!ctx->aux) {
+        int rc = grace_b200_create(&ctx->aux, ctx->device);
+        if (rc) return rc;
+        GB_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    }
+    cudaStream_t sb = ctx->aux_stream;
+    int rc = tiles_reserve(ctx, hit_budget, tile);
+    if (rc) return rc;
+    TileBufs B[2];
+    {
+        const size_t per_set = ctx->tile_bytes / 2;
+        for (int k = 0; k < 2; ++k) {
+            char* p = ctx->tile_mem + k * per_set;
+            B[k].offsets = (int*)p; p += gb_align(tile * 4);
+            B[k].idx = (int*)p; p += gb_align(hit_budget * 4);
+            B[k].integ = (float*)p; p += gb_align(hit_budget * 4);
+            B[k].dist = (float*)p;
+            GB_CUDA(cudaEventCreateWithFlags(&B[k].filled, cudaEventDisableTiming));
+            GB_CUDA(cudaEventCreateWithFlags(&B[k].consumed, cudaEventDisableTiming));
+        }
+    }
+    auto cleanup = [&](int code) {
+        cudaStreamSynchronize(sb);
+        cudaStreamSynchronize(sa);
+        for (int k = 0; k < 2; ++k) { cudaEventDestroy(B[k].filled); cudaEventDestroy(B[k].consumed); }
+        return code;
+    };
+    long long grand = 0;
+    size_t first = 0;           // first ray of the tile being counted
+    int set = 0;
+    bool used[2] = { false, false };
+    // pending = the tile whose fill has been enqueued and whose sort has not
+    bool have_pending = false;
+    size_t p_first = 0, p_m = 0; long long p_total = 0; int p_set = 0;
+    while (first < n_rays || have_pending) {
+        size_t m = 0;
+        bool counting = false;
+        if (first < n_rays) {
+            m = tile < n_rays - first ? tile : n_rays - first;
+            // the offsets of this set were last read by the consumer of two tiles ago
+            if (used[set]) GB_CUDA(cudaStreamWaitEvent(sa, B[set].consumed, 0));
+            rc = hits_count_enqueue(ctx, d_rays + first, m, d_spheres4, n, tree, 0, B[set].offsets, sa);
+            if (rc) return cleanup(rc);
+            counting = true;
+        }
+        if (have_pending) {     // sort + consume the previous tile while this one is being counted
+            GB_CUDA(cudaStreamWaitEvent(sb, B[p_set].filled, 0));
+            if (p_total > 0) {
+                rc = grace_b200_sort_by_distance(ctx->aux, B[p_set].dist, B[p_set].offsets, p_m, (size_t)p_total, B[p_set].idx,
+                                                 B[p_set].integ, (void*)sb);
+                if (rc) return cleanup(rc);
+            }
+            if (consume) {
+                rc = consume(user, p_first, p_m, B[p_set].offsets, p_total, B[p_set].idx, B[p_set].integ, B[p_set].dist, (void*)sb);
+                if (rc) return cleanup(gb_set_error(rc, "the tile consumer returned %d", rc));
+            }
+            GB_CUDA(cudaEventRecord(B[p_set].consumed, sb));
+            have_pending = false;
+        }
+        if (!counting) break;
+        long long total = 0;
+        if ((rc = hits_count_finish(ctx, &total, sa))) return cleanup(rc);
+        if ((unsigned long long)total > hit_budget) {
+            if (m <= 32) return cleanup(gb_set_error(GRACE_B200_ERANGE, "one packet of 32 rays has %lld hits: raise the hit budget (%zu)", total, hit_budget));
+            tile = (m / 2 + 31) / 32 * 32;       // halve and count again
+            continue;
+        }
+        if (total > 0) {
+            rc = grace_b200_trace_hits_fill_f4(ctx, d_rays + first, m, d_spheres4, n, tree, B[set].offsets, B[set].idx, B[set].integ,
+                                               B[set].dist, (void*)sa);
+            if (rc) return cleanup(rc);
+        }
+        GB_CUDA(cudaEventRecord(B[set].filled, sa));
+        used[set] = true;
+        have_pending = true; p_first = first; p_m = m; p_total = total; p_set = set;
+        grand += total;
+        first += m;
+        set ^= 1;
+    }
+    if (h_total_hits) *h_total_hits = grand;
+    return cleanup(GRACE_B200_OK);
 }
 
 int grace_b200_sort_by_distance(grace_b200_ctx* ctx, float* d_hit_distances, const int* d_ray_offsets,

@@ -126,6 +126,35 @@ GRACE_HOST void trace_with_sentinels_sph(const RayVec& d_rays, const SphereVec& 
                         true, index_sentinel, (float)integral_sentinel, (float)distance_sentinel);
 }
 
+// Not in the reference: sorted hit lists of a ray set too large for one trace_sph call (a 4096^2
+// projection of 2^24 particles has ~5e10 hits; trace_sph's offsets are int, cuda/trace_sph.cuh:117),
+// streamed in ray tiles: trace_sph + sort_by_distance per tile in library-owned buffers of
+// `hit_budget` hits, then
+//     consume(size_t first_ray, size_t n_rays, const int* d_ray_offsets, long long n_hits,
+//             const int* d_hit_indices, const float* d_hit_integrals, const float* d_hit_distances,
+//             cudaStream_t stream)
+// which must enqueue its work on `stream`; it overlaps the counting traversal of the next tile.
+// Returns the total number of hits.
+template <typename RayVec, typename SphereVec, typename Consume, detail::if_elem<SphereVec, float4> = 0>
+GRACE_HOST long long trace_sorted_tiles_sph(const RayVec& d_rays, const SphereVec& d_spheres, const Tree& d_tree,
+                                            const size_t hit_budget, Consume consume, const size_t rays_per_tile = 0)
+{
+    struct Tramp {
+        static int call(void* user, size_t first_ray, size_t n_rays, const int* off, long long n_hits, const int* idx,
+                        const float* integ, const float* dist, void* stream)
+        {
+            (*static_cast<Consume*>(user))(first_ray, n_rays, off, n_hits, idx, integ, dist, (cudaStream_t)stream);
+            return 0;
+        }
+    };
+    const grace_b200_tree t = detail::tree_view(d_tree);
+    long long total = 0;
+    GRACE_B200_CHECK(grace_b200_trace_sorted_tiles_f4(detail::context(), reinterpret_cast<const grace_b200_ray*>(detail::raw(d_rays.data())), d_rays.size(),
+                                                      detail::f4(detail::raw(d_spheres.data())), d_spheres.size(), &t, hit_budget,
+                                                      rays_per_tile, &Tramp::call, &consume, &total, nullptr));
+    return total;
+}
+
 } // namespace grace
 
 #ifdef __CUDACC__

@@ -291,6 +291,28 @@ int grace_b200_sort_by_distance(grace_b200_ctx* ctx, float* d_hit_distances,
                                 const int* d_ray_offsets, size_t n_rays, size_t total_hits,
                                 int* d_hit_indices, void* d_hit_data, void* stream);
 
+/* Sorted hit lists of a ray set too large for one trace_sph call, streamed in ray tiles
+ * (replaces: the loop a caller of trace_sph + sort_by_distance has to write around the reference's
+ * 32-bit offsets, cuda/trace_sph.cuh:112-168, cuda/sort.cuh:100-131; BASELINE config 4: a 4096^2
+ * projection of 2^24 particles has ~5e10 hits).  Per tile of rays: count, scan, fill,
+ * sort_by_distance, then `consume` -- all in library-owned buffers sized by hit_budget (hits per
+ * tile, < 2^31; 12 bytes each, two sets) that are reused for every tile and kept by the context.
+ * rays_per_tile (multiple of 32; 0 = 65536) is halved whenever a tile would exceed the budget.
+ * `consume` is called once per tile, in ray order, with the tile's first ray, its ray count, the
+ * exclusive offsets into the tile's lists, the number of hits and the three sorted arrays (device
+ * memory, valid until it returns) and a stream: it must enqueue its work on THAT stream (not the
+ * caller's) and may not call back into the library with this context; a non-zero return aborts.
+ * The sort and the consumer of tile k overlap the counting traversal of tile k + 1.
+ * *h_total_hits (may be NULL) receives the number of hits of all tiles.  Synchronises both streams. */
+typedef int (*grace_b200_hits_tile_fn)(void* user, size_t first_ray, size_t n_rays, const int* d_ray_offsets,
+                                       long long n_hits, const int* d_hit_indices, const float* d_hit_integrals,
+                                       const float* d_hit_distances, void* stream);
+int grace_b200_trace_sorted_tiles_f4(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, size_t n_rays,
+                                     const float* d_spheres4, size_t n, const grace_b200_tree* tree,
+                                     size_t hit_budget, size_t rays_per_tile,
+                                     grace_b200_hits_tile_fn consume, void* user,
+                                     long long* h_total_hits, void* stream);
+
 /* The 51-entry kernel line-integral table (cuda/trace_sph.cuh:22-50). */
 const double* grace_b200_kernel_integral_table(int* n_table);
 

@@ -164,9 +164,88 @@ def test_config3_trace_full_size(gb, orc, snap24):
     assert np.array_equal(orc.brute_cumulative(h_r, h_s).view(np.uint32), cum[pick].cpu().numpy().view(np.uint32))
 
 
+def _ortho_rays(gb, s, side):
+    mins = [float(v) for v in gb.min_vec4(s).cpu()]
+    maxs = [float(v) for v in gb.max_vec4(s).cpu()]
+    cx, cy, cz = [(mins[k] + maxs[k]) / 2 for k in range(3)]
+    span = [maxs[k] - mins[k] for k in range(3)]
+    span[0] = span[1] = max(span[0], span[1])
+    rays = gb.orthographic_projection_rays(None, side, side, (cx, cy, span[2]), (cx, cy, cz), (0, 1, 0),
+                                           span[1], 2 * span[2])
+    return rays, span
+
+
+def test_config4_sorted_hit_lists_whole_image(gb, orc, snap24):
+    """BASELINE config 4: per-ray sorted hit lists of the WHOLE 4096 x 4096 orthographic image of 2^24
+    particles (~1e10 hits at this snapshot's depth), streamed through trace_sorted_tiles in tiles under a hit
+    budget (cuda/trace_sph.cuh:112-168 + cuda/sort.cuh:100-131 per tile).  Every tile: sorted, and the
+    integrals of each list add up to the ray's column density (1e-5); four sub-ranges of different tiles are
+    compared value for value with the lists of the reference's own CUDA implementation."""
+    import refrun
+    raw, s, tree = snap24
+    side = 4096
+    rays, span = _ortho_rays(gb, s, side)
+    r = side * side
+    img = torch.empty(r, dtype=torch.float32, device="cuda")
+    gb.trace_cumulative_sph(rays, s, tree, img)
+    probes = [0, 5 * 65536 + 2048, 128 * 65536, 255 * 65536 + 4096]       # first ray of four 2048-ray ranges
+    seen = {"tiles": 0, "rays": 0, "bad_sorted": 0, "max_rel": 0.0, "kept": {}}
+
+    def consume(first, off, idx, integ, dist):
+        m = off.numel()
+        seen["tiles"] += 1
+        seen["rays"] += m
+        n_hits = dist.numel()
+        ends = torch.cat([off[1:], torch.tensor([n_hits], dtype=torch.int32, device=off.device)]).long()
+        if n_hits:
+            # sortedness: a descent inside a segment is an error
+            desc = (dist[1:] < dist[:-1])
+            boundary = torch.zeros(n_hits, dtype=torch.bool, device=off.device)
+            boundary[off[off < n_hits].long()] = True
+            seen["bad_sorted"] += int((desc & ~boundary[1:]).sum())
+            # the list reproduces the column density
+            cs = torch.cat([torch.zeros(1, dtype=torch.float64, device=off.device), integ.double().cumsum(0)])
+            sums = cs[ends] - cs[off.long()]
+            ref = img[first:first + m].double()
+            rel = ((sums - ref).abs() / ref.abs().clamp_min(1e-30))[ref > 0]
+            if rel.numel():
+                seen["max_rel"] = max(seen["max_rel"], float(rel.max()))
+        for p in probes:
+            if first <= p < first + m:
+                lo = p - first
+                hi = min(lo + 2048, m)
+                a, b = int(off[lo]), (int(off[hi]) if hi < m else n_hits)
+                seen["kept"][p] = (hi - lo, (off[lo:hi] - off[lo]).cpu().numpy(), idx[a:b].cpu().numpy(),
+                                   integ[a:b].cpu().numpy(), dist[a:b].cpu().numpy())
+
+    total = gb.trace_sorted_tiles(rays, s, tree, hit_budget=1 << 28, consume=consume, rays_per_tile=65536)
+    torch.cuda.synchronize()
+    assert gb.device_error() == 0
+    assert seen["rays"] == r and seen["tiles"] >= 256
+    assert seen["bad_sorted"] == 0
+    assert seen["max_rel"] < 1e-5, seen["max_rel"]
+    assert total > 5e9
+    assert len(seen["kept"]) == len(probes)
+    if not refrun.available():
+        pytest.skip("oracle/_ref/ref_driver not built: comparison with the reference CUDA lists skipped")
+    h_raw = raw.cpu().numpy()
+    for p, (m, off, idx, integ, dist) in seen["kept"].items():
+        ref, _ = refrun.run(h_raw, rays[p:p + m].cpu().numpy(), 32, 30, iters=0, lists=True, timeout=900)
+        assert np.array_equal(ref["offsets"], off)
+        ends = np.append(off[1:], len(dist))
+        assert np.array_equal(ref["hit_dist"].view(np.uint32), dist.view(np.uint32))
+        # equal distances may come in either order: compare (distance, index, integral) per ray as sorted sets
+        for a, b in zip(off[::16], ends[::16]):
+            o1 = np.lexsort((idx[a:b], dist[a:b]))
+            o2 = np.lexsort((ref["hit_idx"][a:b], ref["hit_dist"][a:b]))
+            assert np.array_equal(idx[a:b][o1], ref["hit_idx"][a:b][o2])
+            assert np.array_equal(integ[a:b][o1].view(np.uint32), ref["hit_integral"][a:b][o2].view(np.uint32))
+
+
 def test_config4_projection_full_size(gb, orc, snap24):
     """4096 x 4096 orthographic column-density image (tests/project_gadget/project_gadget.cu:
-    66-80, tests/helper/rays.cuh:55-79) + sorted hit lists on one tile of rays."""
+    66-80, tests/helper/rays.cuh:55-79): total mass, rows re-traced with the reference's packet schedule,
+    brute force on sampled pixels.  (The sorted hit lists of the image: the test above.)"""
     raw, s, tree = snap24
     side = 4096
     mins = [float(v) for v in gb.min_vec4(s).cpu()]
