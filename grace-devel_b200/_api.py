@@ -163,6 +163,9 @@ def _dp(t):
 def _need(t, dtype, what, last=None):
     if not (isinstance(t, torch.Tensor) and t.is_cuda and t.is_contiguous() and t.dtype == dtype):
         raise TypeError("%s must be a contiguous CUDA tensor of dtype %s" % (what, dtype))
+    if t.device.index != torch.cuda.current_device():
+        # the context, its workspace and the stream are those of the current device
+        raise ValueError("%s lives on %s but the current CUDA device is %d" % (what, t.device, torch.cuda.current_device()))
     if last is not None and (t.dim() != 2 or t.shape[1] != last):
         raise TypeError("%s must have shape [n, %d]" % (what, last))
     return t
@@ -281,6 +284,8 @@ def morton_keys_sph(d_spheres, d_keys, bot=None, top=None):
     n = d_spheres.shape[0]
     if d_keys.dtype not in (torch.int32, torch.int64) or d_keys.numel() != n:
         raise TypeError("d_keys must be int32 (30-bit) or int64 (63-bit) of length N")
+    if (bot is None) != (top is None):
+        raise ValueError("bot and top must be given together")
     ctx = context()
     if bot is None:
         b6 = torch.empty(6, dtype=torch.float32, device=d_spheres.device)
@@ -336,7 +341,8 @@ def euclidean_deltas_sph(d_spheres, d_deltas):
     """cuda/build_sph.cuh:87-93."""
     _need(d_spheres, torch.float32, "d_spheres", 4)
     _need(d_deltas, torch.float32, "d_deltas")
-    assert d_deltas.numel() == d_spheres.shape[0] + 1
+    if d_deltas.numel() != d_spheres.shape[0] + 1:
+        raise ValueError("d_deltas must hold N + 1 elements")
     _check(_d_euclid(context(), _dp(d_spheres), d_spheres.shape[0], _dp(d_deltas), _stream()))
 
 
@@ -344,13 +350,17 @@ def surface_area_deltas_sph(d_spheres, d_deltas):
     """cuda/build_sph.cuh:97-103."""
     _need(d_spheres, torch.float32, "d_spheres", 4)
     _need(d_deltas, torch.float32, "d_deltas")
-    assert d_deltas.numel() == d_spheres.shape[0] + 1
+    if d_deltas.numel() != d_spheres.shape[0] + 1:
+        raise ValueError("d_deltas must hold N + 1 elements")
     _check(_d_sarea(context(), _dp(d_spheres), d_spheres.shape[0], _dp(d_deltas), _stream()))
 
 
 def XOR_deltas_sph(d_morton_keys, d_deltas):
     """cuda/build_sph.cuh:107-114."""
-    assert d_morton_keys.dtype == d_deltas.dtype and d_deltas.numel() == d_morton_keys.numel() + 1
+    if d_morton_keys.dtype not in (torch.int32, torch.int64) or d_morton_keys.dtype != d_deltas.dtype:
+        raise TypeError("keys and deltas must both be int32 (30-bit keys) or int64 (63-bit keys)")
+    if d_deltas.numel() != d_morton_keys.numel() + 1:
+        raise ValueError("d_deltas must hold N + 1 elements")
     fn = _d_xor32 if d_morton_keys.dtype == torch.int32 else _d_xor64
     _check(fn(context(), _dp(d_morton_keys), d_morton_keys.numel(), _dp(d_deltas), _stream()))
 
@@ -399,14 +409,16 @@ def _trace_args(d_rays, d_spheres, d_tree):
 def trace_hitcounts_sph(d_rays, d_spheres, d_tree, d_hit_counts):
     """cuda/trace_sph.cuh:58-79.  ValueError unless len(rays) % 32 == 0."""
     _need(d_hit_counts, torch.int32, "d_hit_counts")
-    assert d_hit_counts.numel() >= d_rays.shape[0]
+    if d_hit_counts.numel() < d_rays.shape[0]:
+        raise ValueError("d_hit_counts holds fewer elements than there are rays")
     _check(_t_counts(*_trace_args(d_rays, d_spheres, d_tree), _dp(d_hit_counts), _stream()))
 
 
 def trace_cumulative_sph(d_rays, d_spheres, d_tree, d_cumulated):
     """cuda/trace_sph.cuh:82-109."""
     _need(d_cumulated, torch.float32, "d_cumulated")
-    assert d_cumulated.numel() >= d_rays.shape[0]
+    if d_cumulated.numel() < d_rays.shape[0]:
+        raise ValueError("d_cumulated holds fewer elements than there are rays")
     _check(_t_cum(*_trace_args(d_rays, d_spheres, d_tree), _dp(d_cumulated), _stream()))
 
 

@@ -375,6 +375,19 @@ __device__ __forceinline__ void rt_walk(int cur, int sp, int* my_stack, int* lst
     }
 }
 
+// Largest |coordinate| of any box plane of the tree (the root's child boxes contain all others): part of the
+// padding, see trace_packet.cuh.
+__device__ __forceinline__ float rt_tree_extent(const int4* __restrict__ nodes, int root)
+{
+    const int4* np = nodes + 4 * (size_t)root;
+    float m = 0.0f;
+    for (int k = 1; k < 4; ++k) {
+        const int4 q = __ldg(np + k);
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(__int_as_float(q.x)), fabsf(__int_as_float(q.y))), fmaxf(fabsf(__int_as_float(q.z)), fabsf(__int_as_float(q.w)))));
+    }
+    return m < 3.0e38f ? m : 0.0f;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(RT_THREADS)
 trace_ray_kernel(const grace_b200_ray* __restrict__ rays, int n_packets,
@@ -396,6 +409,7 @@ trace_ray_kernel(const grace_b200_ray* __restrict__ rays, int n_packets,
     int* my_stack = s_stack + threadIdx.x;
     int lstack[RT_LOCAL_DEPTH];
     const int root = __ldg(root_ptr);
+    const float tree_extent = rt_tree_extent(nodes, root);
 
     for (;;) {
         int packet = 0;
@@ -406,7 +420,7 @@ trace_ray_kernel(const grace_b200_ray* __restrict__ rays, int n_packets,
         const grace_b200_ray ray = rays[ray_index];
         const float ix = __fdiv_rn(1.0f, ray.dx), iy = __fdiv_rn(1.0f, ray.dy),
                     iz = __fdiv_rn(1.0f, ray.dz);
-        const float pad = 64.0f * 5.9604645e-8f * (fabsf(ray.ox) + fabsf(ray.oy) + fabsf(ray.oz) + fabsf(ray.length));
+        const float pad = 64.0f * 5.9604645e-8f * (fabsf(ray.ox) + fabsf(ray.oy) + fabsf(ray.oz) + fabsf(ray.length) + tree_extent);
         const float lox = ray.ox + pad, loy = ray.oy + pad, loz = ray.oz + pad;
         const float hix = ray.ox - pad, hiy = ray.oy - pad, hiz = ray.oz - pad;
         int count = 0;

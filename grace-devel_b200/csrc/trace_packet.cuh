@@ -869,6 +869,18 @@ trace_packet_kernel(const __grid_constant__ PkArgs P, const __grid_constant__ Pk
     const int n_nodes = P.n_nodes;
     const int root = __ldg(P.root_ptr);
     const unsigned lt = gb_lanemask_lt();
+    // largest |coordinate| of any box plane of the tree (the root's two child boxes contain all others):
+    // the planes are c -/+ h rounded to float, i.e. off by up to 2^-24 of their own magnitude, which the
+    // padding of the slab test has to cover as well -- also for spheres much larger than the rays are long
+    float tree_extent;
+    {
+        const int4* np = nodes + 4 * (size_t)root;
+        const int4 n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+        tree_extent = fmaxf(fmaxf(fmaxf(fabsf(__int_as_float(n1.x)), fabsf(__int_as_float(n1.y))), fmaxf(fabsf(__int_as_float(n1.z)), fabsf(__int_as_float(n1.w)))),
+                            fmaxf(fmaxf(fabsf(__int_as_float(n2.x)), fabsf(__int_as_float(n2.y))), fmaxf(fabsf(__int_as_float(n2.z)), fabsf(__int_as_float(n2.w)))));
+        tree_extent = fmaxf(tree_extent, fmaxf(fmaxf(fabsf(__int_as_float(n3.x)), fabsf(__int_as_float(n3.y))), fmaxf(fabsf(__int_as_float(n3.z)), fabsf(__int_as_float(n3.w)))));
+        if (!(tree_extent < 3.0e38f)) tree_extent = 0.0f;      // non-finite boxes: nothing sensible to add
+    }
     const bool donating = SUB && !PROF && !FOLD && T.kind == PK_KIND_PACKETS && T.state != nullptr;
     const int n_units = FOLD ? __ldg(T.n_roots)
                       : T.kind == PK_KIND_TASKS ? min(__ldg(T.n_tasks_in), T.tasks_cap) : P.n_packets;
@@ -919,7 +931,7 @@ trace_packet_kernel(const __grid_constant__ PkArgs P, const __grid_constant__ Pk
         S.ix = pk_finite_rcp(ray.dx); S.iy = pk_finite_rcp(ray.dy); S.iz = pk_finite_rcp(ray.dz);
         S.len = ray.length;
         const float pad = 64.0f * 5.9604645e-8f *
-                          (fabsf(ray.ox) + fabsf(ray.oy) + fabsf(ray.oz) + fabsf(ray.length));
+                          (fabsf(ray.ox) + fabsf(ray.oy) + fabsf(ray.oz) + fabsf(ray.length) + tree_extent);
         // t_bottom = fma(b, inv, cb), t_top = fma(t, inv, ct) with the box grown by pad
         S.cbx = -(ray.ox + pad) * S.ix; S.ctx = -(ray.ox - pad) * S.ix;
         S.cby = -(ray.oy + pad) * S.iy; S.cty = -(ray.oy - pad) * S.iy;

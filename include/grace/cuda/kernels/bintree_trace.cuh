@@ -142,6 +142,10 @@ GRACE_HOST void trace(const Ray* d_rays, const size_t N_rays, const TPrimitive* 
         d_primitives, d_tree.max_per_leaf, user_smem_bytes, d_scalars.data(), d_scalars.data() + 1, init, intersect,
         on_hit, ray_entry, ray_exit);
     GRACE_CUDA_CHECK(cudaPeekAtLastError());
+    // releasing d_scalars waits for the kernel anyway: look at the stack-overflow flag first, results of an
+    // overflowed walk are short (the reference asserts in the kernel, debug builds only: bintree_trace.cuh:162-164)
+    if (d_scalars[1] != 0)
+        throw std::runtime_error("grace::trace: traversal stack overflow (tree deeper than GENERIC_STACK_SIZE allows)");
 }
 
 template <typename RayData, typename RayVec, typename PrimVec, typename Init, typename Intersection, typename OnHit,

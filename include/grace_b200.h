@@ -14,9 +14,13 @@
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*; NULL is
  *     the legacy default stream).  Calls that must return a count to the host
  *     (documented per function) synchronise that stream, the others do not;
- *   - temporaries come from the context's workspace arena, which only grows;
- *     a context must not be used from two host threads at once (the reference
- *     is not re-entrant either: cuda/kernels/bintree_trace.cuh:37-38);
+ *   - temporaries come from the context's workspace arena, which only grows, and from a block
+ *     of device scalars (tickets, counters, the traversal's error flag): ONE STREAM PER
+ *     CONTEXT AT A TIME.  Calls on the same context are ordered by enqueueing them on the same
+ *     stream; work on two streams (or from two host threads) needs two contexts, or the caller
+ *     must order the second stream behind the first (event) before its next call.  Workspace
+ *     growth synchronises the device: pre-size it (grace_b200_reserve) before capturing a
+ *     CUDA graph.  (The reference is not re-entrant either: cuda/kernels/bintree_trace.cuh:37-38);
  *   - return value: 0 = success, otherwise a GRACE_B200_E* code;
  *     grace_b200_last_error() gives the message of the calling thread's last
  *     failure.  The C++ shim maps GRACE_B200_EINVAL to std::invalid_argument and
