@@ -522,6 +522,39 @@ def run_b200(args):
                             "the same particles and rays: grid cap as shipped (kernel_config.h:11 MAX_BLOCKS = 112) and lifted to "
                             "148 x 8 blocks ('tuned'); CUDA events, 3 steps")
 
+    # ---- BASELINE configs[2] literally (2^20 rays, the round-1 bench workload), next to the same two reference builds ----
+    small = None
+    if world == 1 and args.log2_rays != 20:
+        r20 = 1 << 20
+        rays20 = torch.empty((r20, 7), dtype=torch.float32, device=dev)
+        gb.uniform_random_rays(rays20, c, c, c, length, 1234)
+        out20 = torch.empty(r20, dtype=torch.float32, device=dev)
+        ts = []
+        for k in range(8):
+            flush.fill_(k)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            gb.trace_cumulative_sph(rays20, spheres, tree, out20)
+            b.record(stream)
+            torch.cuda.synchronize()
+            if k >= 3:
+                ts.append(a.elapsed_time(b))
+        ms20 = statistics.mean(ts)
+        small = {"workload": "2^24 particles, 2^20 isotropic rays (BASELINE configs[2] as written; BENCH_r01's workload)",
+                 "ms_per_step": ms20, "value": r20 / ms20 / 1e3, "unit": "Mrays/s"}
+        if not args.no_reference_cuda:
+            class A20:      # the same reference programs on the smaller ray set
+                log2_particles, log2_rays, max_per_leaf = args.log2_particles, 20, args.max_per_leaf
+            for name, tuned in (("reference_cuda_as_shipped", False), ("reference_cuda_tuned", True)):
+                try:
+                    info = run_ref_bench(A20, 3, 1, 1, tuned=tuned)
+                    if info is not None:
+                        small[name] = {"ms_per_step": info["ms_per_step"], "value": r20 / info["ms_per_step"] / 1e3,
+                                       "speedup_of_this_repo": info["ms_per_step"] / ms20}
+                except Exception as e:
+                    small[name] = {"unavailable": str(e)[:200]}
+        del rays20, out20
+
     line = {
         "metric": METRIC, "value": value, "unit": "Mrays/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -540,6 +573,7 @@ def run_b200(args):
         "cpu_baseline": cpu,
         "reference_cuda": ref_cuda,
         "build": build_info,
+        "config3_2p20_rays": small,
         "config5": config5,
         "wall_s_timed_region": t_wall,
         "n_leaves": tree.n_leaves,

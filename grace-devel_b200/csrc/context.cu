@@ -3,6 +3,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -67,6 +68,16 @@ int grace_b200_create(grace_b200_ctx** out, int device)
     cudaDeviceProp prop;
     GB_CUDA(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
+    // Part of the (126 MB on B200) L2 can be set aside for data marked "persisting": the trace launches mark
+    // the node array (54 MB at 2^24 particles), whose records every step of every packet waits for.
+    ctx->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
+    ctx->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+    {
+        const char* e = getenv("GRACE_B200_L2_PERSIST");
+        ctx->l2_persist = e ? atoi(e) : 0;
+        if (ctx->l2_persist && ctx->l2_persist_max)
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, ctx->l2_persist_max);
+    }
     GB_CUDA(cudaMalloc((void**)&ctx->d_scalars, GB_SC_COUNT * sizeof(int)));
     GB_CUDA(cudaMemset(ctx->d_scalars, 0, GB_SC_COUNT * sizeof(int)));
     GB_CUDA(cudaMallocHost((void**)&ctx->h_pinned, GB_SC_COUNT * sizeof(int)));

@@ -474,6 +474,28 @@ int launch_packet(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, int n_packe
     // launches, 0 = packets, then suspended traversals resumed as tasks over 8, 2 and finally 1 ray(s).
     const bool split = (d_prof == nullptr) && (ctx->trace_budget & 0x3fffffff) > 0 && n_packets >= 2;
     GB_CUDA(cudaMemsetAsync(ctx->d_scalars + GB_SC_ERRFLAG, 0, sizeof(int), st));
+    struct L2Window {       // node array persisting in L2 for the launches of this call
+        cudaStream_t st; bool on;
+        L2Window(grace_b200_ctx* c, const grace_b200_tree* t, cudaStream_t s) : st(s), on(false)
+        {
+            if (!c->l2_persist || !c->l2_persist_max || !c->l2_window_max) return;
+            cudaStreamAttrValue a = {};
+            a.accessPolicyWindow.base_ptr = const_cast<void*>(t->d_nodes);
+            a.accessPolicyWindow.num_bytes = std::min<size_t>((size_t)(t->n_leaves - 1) * 64, c->l2_window_max);
+            a.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)c->l2_persist_max / (double)a.accessPolicyWindow.num_bytes);
+            a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            on = cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &a) == cudaSuccess;
+            if (!on) cudaGetLastError();
+        }
+        ~L2Window()
+        {
+            if (!on) return;
+            cudaStreamAttrValue a = {};
+            a.accessPolicyWindow.num_bytes = 0;
+            cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &a);
+        }
+    } l2_window(ctx, tree, st);
     PkArgs P;
     P.rays = d_rays; P.n_packets = n_packets; P.spheres = (const float4*)d_spheres4;
     P.nodes = (const int4*)tree->d_nodes; P.leaves = (const int4*)tree->d_leaves;

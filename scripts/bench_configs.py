@@ -95,39 +95,36 @@ if 4 in want:
     t_cum = timed(lambda: gb.trace_cumulative_sph(rays, s, tree, cum), reps=2)
     area = (span[0] / side) * (span[1] / side)
     mass = float(cum.double().sum().item()) * area       # each particle's kernel integrates to 1 over the plane
-    # sorted hit lists in ray tiles
-    tile = args.tile_rays; n_tiles = 8
-    t_lists = t_sort = 0.0; hits = 0
-    for k in range(n_tiles):
-        sub = rays[(k * (r // n_tiles)) // 32 * 32:][:tile]
-        off = torch.empty(tile, dtype=torch.int32, device="cuda")
-        # untimed first call: the three hit arrays of this tile's size are then in torch's caching
-        # allocator and the timed call does not pay for cudaMalloc
-        idx, integ, dist = gb.trace_sph(sub, s, tree, off)
-        del idx, integ, dist
-        a, b, c2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        a.record(); idx, integ, dist = gb.trace_sph(sub, s, tree, off)
-        b.record(); gb.sort_by_distance(dist, off, idx, integ)
-        c2.record(); torch.cuda.synchronize()
-        if k == 1:   # the step after the path: optical-depth style scan along the sorted lists (8 B/hit)
+    # sorted hit lists of the WHOLE image, streamed in ray tiles by the library (count -> scan -> fill -> sort ->
+    # consumer per tile, reused buffers, sort of tile k overlapping the count of tile k + 1)
+    tile = args.tile_rays
+    seen = dict(tiles=0, hits=0, bad=0)
+    scan_info = {}
+
+    def consume(first, off, idx, integ, dist):
+        seen["tiles"] += 1
+        seen["hits"] += dist.numel()
+        if seen["tiles"] == 2 and dist.numel():   # the step after the path: optical-depth style scan along the sorted lists
             tau = torch.empty_like(integ)
             t_scan = timed(lambda: gb.exclusive_segmented_scan(off, integ, tau), reps=3)
-            scan_info = dict(hits=idx.numel(), ms=t_scan, ghits_s=idx.numel() / t_scan / 1e6,
+            scan_info.update(hits=idx.numel(), ms=t_scan, ghits_s=idx.numel() / t_scan / 1e6,
                              hbm_frac=8.0 * idx.numel() / (t_scan * 1e-3) / 1e9 / peak)
-            del tau
-        t_lists += a.elapsed_time(b); t_sort += b.elapsed_time(c2); hits += idx.numel()
-        if k == 0:   # sortedness + the list reproduces the column density
-            o = off.cpu().numpy(); d = dist.cpu().numpy(); ends = np.append(o[1:], len(d))
-            ok_sorted = all(np.all(np.diff(d[b_:e_]) >= 0) for b_, e_ in zip(o[::64], ends[::64]))
-            sums = np.add.reduceat(np.append(integ.cpu().numpy().astype(np.float64), 0.0), np.minimum(o, len(d)))[: len(o)]
-            sums[ends == o] = 0.0
-            ref = torch.empty(tile, dtype=torch.float32, device="cuda"); gb.trace_cumulative_sph(sub, s, tree, ref)
-            refn = ref.cpu().numpy().astype(np.float64)
-            rel = float(np.max(np.abs(sums - refn) / np.maximum(np.abs(refn), 1e-30)))
-        del idx, integ, dist
+        if seen["tiles"] % 64 == 1 and dist.numel():   # sortedness of a sample of tiles
+            n_hits = dist.numel()
+            boundary = torch.zeros(n_hits, dtype=torch.bool, device=off.device)
+            boundary[off[off < n_hits].long()] = True
+            seen["bad"] += int(((dist[1:] < dist[:-1]) & ~boundary[1:]).sum())
+
+    gb.trace_sorted_tiles(rays[: 4 * tile], s, tree, 1 << 28, lambda *a: None, tile)      # buffers allocated, kernels loaded
+    t0 = time.perf_counter()
+    total_hits = gb.trace_sorted_tiles(rays, s, tree, 1 << 28, consume, tile)
+    torch.cuda.synchronize()
+    t_lists_all = (time.perf_counter() - t0) * 1e3
+    ok_sorted = seen["bad"] == 0
+    n_tiles = seen["tiles"]; hits = total_hits; t_lists = t_lists_all; t_sort = 0.0; rel = None
     out["config4_project_gadget"] = dict(n=n, image=[side, side], gen_rays_ms=t_gen, cumulative_ms=t_cum, mrays_s_cumulative=r / t_cum / 1e3,
         mass_recovered_over_n=mass / n, lists=dict(tiles=n_tiles, rays_per_tile=tile, hits=hits, trace_ms=t_lists, sort_ms=t_sort,
-        mrays_s=n_tiles * tile / (t_lists + t_sort) / 1e3, mhits_s=hits / (t_lists + t_sort) / 1e3, sorted=bool(ok_sorted),
+        whole_image=True, wall_ms=t_lists_all, mrays_s=r / t_lists_all / 1e3, mhits_s=hits / t_lists_all / 1e3, sorted=bool(ok_sorted),
         list_sum_vs_cumulative_max_rel=rel), exclusive_segmented_scan=scan_info)
     del rays, cum
 

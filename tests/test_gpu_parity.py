@@ -490,3 +490,31 @@ def test_segmented_scans(gb, count, max_seg, empty):
         flags[1] = 1
         flags[2:] = off[2:] != off[1:-1]
     assert np.array_equal(host(segs), np.cumsum(flags)[seg_id])
+
+
+@pytest.mark.parametrize("nside", [1, 4, 64, 1024])
+def test_healpix_directions_bit_level(gb, orc, nside):
+    """HEALPix NESTED pixel centres (RayVectorGeneration/src/chealpix/chealpix.c:112-126,357-391,459-467):
+    the generator's directions against the oracle's restatement of pix2vec_nest rounded to float.  The double
+    arithmetic is the same; sin / cos of the device library may differ from libm's in the last bit of a double,
+    which survives rounding to float in well under one direction in a thousand -- those must be 1 ulp apart."""
+    npix = 12 * nside * nside
+    first = 0 if npix <= 4096 else 5 * nside * nside - 1000          # across a base-face boundary
+    n = min(npix, 4096) // 32 * 32 or 32
+    n = min(n, npix - first) // 32 * 32 if npix >= 32 else 0
+    if n == 0:
+        n, first = 0, 0
+        # nside 1: 12 pixels -- rays must come in packets of 32 only for tracing, the generator takes any count
+        rays = gb.healpix_rays(None, nside, 0, 12, 0.5, 0.25, 0.125, 3.0)
+        n = 12
+    else:
+        rays = gb.healpix_rays(None, nside, first, n, 0.5, 0.25, 0.125, 3.0)
+    got = host(rays)
+    ref = orc.pix2vec_nest(nside, np.arange(first, first + n)).astype(np.float32)
+    assert np.array_equal(got[:, 3:], np.tile(np.array([0.5, 0.25, 0.125, 3.0], np.float32), (n, 1)))
+    d = np.abs(got[:, :3].view(np.int32).astype(np.int64) - ref.view(np.int32).astype(np.int64))
+    # +0.0 vs a value that rounds to the smallest denormals cannot happen here: |components| are 0 or >= 1e-7
+    assert d.max() <= 1, d.max()
+    assert (d != 0).mean() < 1e-3
+    # unit length to float precision
+    assert np.abs(np.linalg.norm(got[:, :3].astype(np.float64), axis=1) - 1.0).max() < 2e-7
