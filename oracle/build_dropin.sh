@@ -33,7 +33,9 @@ done
 # the test compares the two builds' outputs instead of expecting PASSED.
 SCRATCH=${TMPDIR:-/tmp}/grace_ref_patched
 [ -d "$SCRATCH/include" ] || python "$HERE/patch_ref.py" "$REF" "$SCRATCH" > /dev/null
-for p in morton_key_kernel/30bit_keys morton_key_kernel/63bit_keys; do
+# ... and the reference's three self-checking programs against its own headers: the gate BASELINE.md 2b puts
+# before the patched reference build is used as a comparator (tests/test_gpu_dropin.py keeps their output)
+for p in morton_key_kernel/30bit_keys morton_key_kernel/63bit_keys tree_traversal/tree_traversal distance_sort/distance_sort integrate/integrate; do
   name=ref_$(echo $p | tr '/' '_')
   $NVCC -arch=sm_100 -O2 -std=c++17 -w -Xcompiler -fopenmp -I "$SCRATCH/include" -I "$SCRATCH/tests" \
       -I "$SCRATCH/include/grace/external/sgpu" "$REF/tests/$p.cu" -o "$OUT/$name" -lcurand > "$OUT/$name.log" 2>&1 \

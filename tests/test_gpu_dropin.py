@@ -124,3 +124,17 @@ def test_profile_one_to_many_rays_gadget(gadget_file):
 def test_project_gadget(gadget_file, tmp_path):
     rc, out = run("project_gadget_project_gadget", 2048, 32, gadget_file)
     assert rc == 0, out[-2000:]
+
+
+@pytest.mark.parametrize("prog,args,needle", [("tree_traversal_tree_traversal", (100000, 312, 32), "PASSED"),
+                                              ("distance_sort_distance_sort", (100000, 80, 32), "sorted correctly"),
+                                              ("integrate_integrate", (), "Normalized volume integral")])
+def test_reference_build_passes_its_own_gate(prog, args, needle):
+    """the CUDA-12-patched build of the REFERENCE (oracle/patch_ref.py) must pass the reference's
+    own self-checking programs on this GPU before it is used as the timing / parity comparator.  The output is
+    kept under gpurun_out/ (copied to profiles/ by the round's profile refresh)."""
+    rc, out = run("ref_" + prog, *args)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "reference_gate_%s.txt" % prog), "w") as f:
+        f.write(out)
+    assert rc == 0 and needle in out, out[-2000:]
