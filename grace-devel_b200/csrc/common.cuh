@@ -23,6 +23,16 @@ struct grace_b200_ctx {
     cudaStream_t aux_stream = nullptr;
     char* tile_mem = nullptr;
     size_t tile_bytes = 0;
+    // one-pass hit lists (trace.cu, hits.cu): the hits the count call recorded in the workspace, for the fill call
+    unsigned long long ws_epoch = 0;        // bumped whenever a call takes more of the arena than its small head
+    int rec_valid = 0;
+    unsigned long long rec_epoch = 0;
+    const void* rec_rays = nullptr; size_t rec_n_rays = 0; const void* rec_offsets = nullptr;
+    alignas(16) unsigned char rec_blob[512] = {};   // launch arguments of the copy launch
+    size_t rec_units = 0;                   // packets of the last recording
+    size_t rec_pool_learned = 0;            // what a recording that overflowed its pool would have needed
+    size_t rec_pool_hint = 0;               // bytes of hit pool the next recording should use (0 = from the ray count)
+    int one_pass_lists = 1;
     size_t leaves_stage_n = 0;       // > 0: the workspace still holds the leaf-level deltas of an albvh_leaves call
     int leaves_stage_delta_type = 0;
     int trace_mode = GRACE_B200_TRACE_PACKET;
@@ -58,6 +68,14 @@ int gb_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 // Returns a pointer to at least `bytes` of workspace (256-byte aligned), growing
 // the arena if needed (growth synchronises the device).  nullptr on failure.
 void* gb_workspace(grace_b200_ctx* ctx, size_t bytes);
+// The first GB_WS_HEAD bytes of the arena are for small helpers (scan states ...): a request that fits
+// there leaves whatever a trace call recorded behind it intact.
+constexpr size_t GB_WS_HEAD = 65536;
+// one-pass hit lists (trace.cu): record the hits while counting / copy them out at the offsets
+int gb_trace_record_f4(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, size_t n_rays, const float* d_spheres4, size_t n,
+                       const grace_b200_tree* tree, int* d_counts, cudaStream_t st);
+int gb_trace_resolve_recorded(grace_b200_ctx* ctx, const int* d_offsets, cudaStream_t st);
+int gb_trace_copy_recorded(grace_b200_ctx* ctx, const int* d_offsets, int* d_idx, float* d_integ, float* d_dist, cudaStream_t st);
 
 #define GB_CUDA(call)                                                         \
     do {                                                                      \

@@ -26,7 +26,9 @@ int gb_cuda_fail(cudaError_t e, const char* what, const char* file, int line)
 
 void* gb_workspace(grace_b200_ctx* ctx, size_t bytes)
 {
+    if (bytes > GB_WS_HEAD) ++ctx->ws_epoch;       // whatever a trace call recorded beyond the head is gone
     if (bytes <= ctx->ws_bytes) return ctx->ws;
+    ++ctx->ws_epoch;
     size_t want = gb_align(bytes + bytes / 8, 1 << 20);
     // Growth: drain outstanding work that may still use the old arena.
     if (cudaDeviceSynchronize() != cudaSuccess) return nullptr;
@@ -73,6 +75,8 @@ int grace_b200_create(grace_b200_ctx** out, int device)
     ctx->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
     ctx->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
     {
+        const char* op = getenv("GRACE_B200_ONE_PASS_LISTS");
+        if (op) ctx->one_pass_lists = atoi(op);
         const char* e = getenv("GRACE_B200_L2_PERSIST");
         ctx->l2_persist = e ? atoi(e) : 0;
         if (ctx->l2_persist && ctx->l2_persist_max)

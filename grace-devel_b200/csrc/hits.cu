@@ -374,7 +374,9 @@ int grace_b200_exclusive_scan_i32(grace_b200_ctx* ctx, const int* d_in, int* d_o
 static int hits_count_enqueue(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, size_t n_rays, const float* d_spheres4,
                               size_t n, const grace_b200_tree* tree, int with_sentinels, int* d_ray_offsets, cudaStream_t st)
 {
-    int rc = grace_b200_trace_hitcounts_f4(ctx, d_rays, n_rays, d_spheres4, n, tree, d_ray_offsets, (void*)st);
+    // one traversal that counts AND records the hits (trace.cu) where it applies, else the plain counting traversal
+    int rc = gb_trace_record_f4(ctx, d_rays, n_rays, d_spheres4, n, tree, d_ray_offsets, st);
+    if (rc) rc = grace_b200_trace_hitcounts_f4(ctx, d_rays, n_rays, d_spheres4, n, tree, d_ray_offsets, (void*)st);
     if (rc) return rc;
     long long* d_total = (long long*)(ctx->d_scalars + GB_SC_TOTAL64);
     rc = run_scan(ctx, d_ray_offsets, d_ray_offsets, n_rays, with_sentinels ? 1 : 0, d_total, st);
@@ -384,6 +386,11 @@ static int hits_count_enqueue(grace_b200_ctx* ctx, const grace_b200_ray* d_rays,
     // its stack or did not terminate are short, and the fill pass would disagree with them
     GB_CUDA(cudaMemcpyAsync(ctx->h_pinned + GB_SC_ERRFLAG, ctx->d_scalars + GB_SC_ERRFLAG, sizeof(int),
                             cudaMemcpyDeviceToHost, st));
+    if (ctx->rec_valid) {     // where the stolen subtrees' hits start; did the hit pool of the recording run dry?
+        if ((rc = gb_trace_resolve_recorded(ctx, d_ray_offsets, st))) return rc;
+        GB_CUDA(cudaMemcpyAsync(ctx->h_pinned + GB_SC_LB, ctx->d_scalars + GB_SC_LB, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        ctx->rec_units = n_rays / 32;
+    }
     return GRACE_B200_OK;
 }
 
@@ -391,6 +398,13 @@ static int hits_count_finish(grace_b200_ctx* ctx, long long* h_total_hits, cudaS
 {
     GB_CUDA(cudaStreamSynchronize(st));
     *h_total_hits = *(long long*)(ctx->h_pinned + GB_SC_TOTAL64);
+    if (ctx->rec_valid && ctx->h_pinned[GB_SC_LB + 7]) {       // counts are right, the recorded lists are not: two passes
+        ctx->rec_valid = 0;
+        // ... and the next recording gets the pool this one would have needed: 16 bytes a hit + a partly filled chunk per unit
+        const size_t units = ctx->rec_units + (size_t)std::max(ctx->h_pinned[GB_SC_LB + 1], 0);
+        const size_t need = (size_t)*h_total_hits * 16 + units * 8192 + ((size_t)64 << 20);
+        ctx->rec_pool_learned = std::min<size_t>(std::max(ctx->rec_pool_learned, need + need / 8), (size_t)64 << 30);
+    }
     GB_REQUIRE(ctx->h_pinned[GB_SC_ERRFLAG] == 0, GRACE_B200_EDEVICE,
                "device-side traversal error %d (1 = stack overflow, 2 = walk did not terminate): hit counts are incomplete",
                ctx->h_pinned[GB_SC_ERRFLAG]);
@@ -458,6 +472,8 @@ int grace_b200_trace_sorted_tiles_f4(grace_b200_ctx* ctx, const grace_b200_ray* 
     cudaStream_t sb = ctx->aux_stream;
     int rc = tiles_reserve(ctx, hit_budget, tile);
     if (rc) return rc;
+    // the counting traversal of a tile also records its hits (16 bytes each, blocks padded): room for a full tile
+    ctx->rec_pool_hint = hit_budget * 24 + ((size_t)64 << 20);
     TileBufs B[2];
     {
         const size_t per_set = ctx->tile_bytes / 2;
@@ -472,6 +488,7 @@ int grace_b200_trace_sorted_tiles_f4(grace_b200_ctx* ctx, const grace_b200_ray* 
         }
     }
     auto cleanup = [&](int code) {
+        ctx->rec_pool_hint = 0;
         cudaStreamSynchronize(sb);
         cudaStreamSynchronize(sa);
         for (int k = 0; k < 2; ++k) { cudaEventDestroy(B[k].filled); cudaEventDestroy(B[k].consumed); }

@@ -29,6 +29,7 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <cstring>
 
 namespace {
 
@@ -37,7 +38,8 @@ constexpr int TR_WARPS = TR_THREADS / 32;
 constexpr int TR_STACK = 96;             // reference STACK_SIZE is 64 (kernel_config.h:13)
 constexpr int N_TABLE = 51;
 
-enum { MODE_COUNT = 0, MODE_CUMULATIVE = 1, MODE_FILL = 2, MODE_STATS = 3, MODE_RAYCOST = 4 };
+enum { MODE_COUNT = 0, MODE_CUMULATIVE = 1, MODE_FILL = 2, MODE_STATS = 3, MODE_RAYCOST = 4,
+       MODE_REC = 5 };      // MODE_REC: hit lists in one traversal (packet kernel only): hits recorded in chunk chains
 
 // Numeric data of cuda/trace_sph.cuh:32-48: line integrals of the Gadget-2 cubic
 // spline at impact parameter b/h = i/50.
@@ -454,8 +456,9 @@ int launch_packet(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, int n_packe
 {
     if (MODE == MODE_STATS || MODE == MODE_RAYCOST) return GRACE_B200_EINVAL;   // other kernels
     constexpr int KMODE = (MODE == MODE_STATS || MODE == MODE_RAYCOST) ? MODE_COUNT : MODE;
-    constexpr bool SUB = KMODE != MODE_FILL;          // subtree donation inside the launch (counts, column densities)
+    constexpr bool SUB = KMODE != MODE_FILL;          // work stealing inside the launch (counts, column densities, recorded hit lists)
     constexpr bool CHAIN = KMODE == MODE_CUMULATIVE;  // ordered term chains + fold launch
+    constexpr bool RECM = KMODE == MODE_REC;          // hit lists in one traversal: hits recorded in chains, copied out by the fill call
     // the per-packet profile counters exist only in a separate MODE_COUNT instantiation
     auto kernel = (KMODE == MODE_COUNT && d_prof) ? trace_packet_kernel<KMODE, M4, KMODE == MODE_COUNT, false>
                                                   : trace_packet_kernel<KMODE, M4, false, false>;
@@ -503,6 +506,7 @@ int launch_packet(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, int n_packe
     P.out_counts = out_counts; P.out_cum = out_cum; P.offsets = offsets;
     P.hit_idx = hit_idx; P.hit_integral = hit_integral; P.hit_dist = hit_dist;
     P.unit_counter = counter; P.err_flag = ctx->d_scalars + GB_SC_ERRFLAG; P.prof = d_prof;
+    if (!split && RECM) return GRACE_B200_EINVAL;      // recording needs the pool: the caller falls back to two passes
     if (!split) {
         PkTasks T = {};
         T.kind = PK_KIND_PACKETS;
@@ -517,13 +521,22 @@ int launch_packet(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, int n_packe
         const int records_cap = 1 << 20;
         const size_t rec_bytes = gb_align((size_t)records_cap * PK_DREC_WORDS * 4);
         const size_t slot_bytes = gb_align((size_t)n_slots * sizeof(int));
-        const size_t roots_bytes = CHAIN ? gb_align((size_t)n_packets * sizeof(int2)) : 0;
-        const size_t rcum_bytes = CHAIN ? gb_align((size_t)n_packets * 32 * sizeof(float)) : 0;
+        const size_t roots_bytes = (CHAIN || RECM) ? gb_align((size_t)n_packets * sizeof(int2)) : 0;
+        const size_t rcum_bytes = (CHAIN || RECM) ? gb_align((size_t)n_packets * 32 * sizeof(float)) : 0;     // hit records: own counts (int)
         // term pool: the terms of stolen work only -- at most the hits of the packets in flight when the
         // tickets run out, i.e. bounded by the grid, not by the ray count.  A dry pool costs time (the
         // fold launch walks the aborted tasks itself), never correctness.
         size_t pool_bytes = 0;
         int pool_cap = 0;
+        if (RECM) {
+            // every hit of the call, 16 bytes each, + one partly filled chunk per unit.  Overflow = this call falls back
+            // to the two-pass fill and the next one asks for what this one would have needed (rec_pool_learned).
+            pool_bytes = ctx->rec_pool_hint ? ctx->rec_pool_hint : ctx->trace_pool_bytes ? ctx->trace_pool_bytes
+                                            : std::min<size_t>(std::max<size_t>((size_t)n_packets * 32 * 32768, (size_t)256 << 20), (size_t)4096 << 20);
+            pool_bytes = std::max(pool_bytes, ctx->rec_pool_learned);
+            pool_cap = (int)std::min<size_t>(pool_bytes / PK_RCH_BYTES, 1u << 30);
+            pool_bytes = gb_align((size_t)pool_cap * PK_RCH_BYTES);
+        }
         if (CHAIN) {
             pool_bytes = ctx->trace_pool_bytes ? ctx->trace_pool_bytes
                                                : std::min<size_t>(std::max<size_t>((size_t)n_packets * 32 * 65536, (size_t)64 << 20),
@@ -532,19 +545,21 @@ int launch_packet(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, int n_packe
             pool_bytes = gb_align((size_t)pool_cap * PK_CH_BYTES);
         }
         const size_t adv_bytes = gb_align(PK_ADV * sizeof(int));
-        char* w = (char*)gb_workspace(ctx, 4096 + rec_bytes + 2 * slot_bytes + adv_bytes + roots_bytes + rcum_bytes + pool_bytes);
+        const size_t order_bytes = RECM ? gb_align((size_t)pool_cap * sizeof(int)) : 0;       // hit records: the copy order
+        char* w = (char*)gb_workspace(ctx, GB_WS_HEAD + rec_bytes + 2 * slot_bytes + adv_bytes + roots_bytes + rcum_bytes + order_bytes + pool_bytes);
         if (!w) return GRACE_B200_ENOMEM;
         int* lb = ctx->d_scalars + GB_SC_LB;
         PkTasks T = {};
         T.kind = PK_KIND_PACKETS;
-        char* p = w + 4096;
+        char* p = w + GB_WS_HEAD;
         T.records = (int*)p; p += rec_bytes;
         T.state = (int*)p; p += slot_bytes;
         T.resp = (int*)p; p += slot_bytes;
         T.adv = (int*)p; p += adv_bytes;
         T.roots = (int2*)p; p += roots_bytes;
         T.root_cum = (float*)p; p += rcum_bytes;
-        T.pool = CHAIN ? p : nullptr;
+        T.order = (int*)p; p += order_bytes;
+        T.pool = (CHAIN || RECM) ? p : nullptr;
         T.n_slots = n_slots;
         T.records_cap = records_cap;
         T.budget = ctx->trace_budget & 0x3fffffff;
@@ -557,10 +572,19 @@ int launch_packet(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, int n_packe
         GB_CUDA(cudaMemsetAsync(T.adv, 0, adv_bytes, st));
         GB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
         // robbed packets and their tasks add into the same cells
-        if (KMODE == MODE_COUNT) GB_CUDA(cudaMemsetAsync(out_counts, 0, (size_t)n_packets * 32 * sizeof(int), st));
+        if (KMODE == MODE_COUNT || RECM) GB_CUDA(cudaMemsetAsync(out_counts, 0, (size_t)n_packets * 32 * sizeof(int), st));
         // the whole grid: the warps that get no packet are the first thieves
         kernel<<<full_grid, PK_THREADS, psmem, st>>>(P, T);
         GB_LAUNCH_CHECK();
+        if (RECM) {      // the copy launch comes with the fill call: keep what it needs
+            static_assert(sizeof(PkArgs) + sizeof(PkTasks) <= sizeof(ctx->rec_blob), "rec_blob too small");
+            T.kind = PK_KIND_FOLD;
+            T.state = nullptr;
+            memcpy(ctx->rec_blob, &P, sizeof(PkArgs));
+            memcpy(ctx->rec_blob + sizeof(PkArgs), &T, sizeof(PkTasks));
+            ctx->rec_valid = 1;
+            ctx->rec_epoch = ctx->ws_epoch;
+        }
         if (CHAIN) {
             auto fold = trace_packet_kernel<KMODE, M4, false, CHAIN>;
             GB_CUDA(cudaFuncSetAttribute(fold, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
@@ -576,10 +600,10 @@ int launch_packet(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, int n_packe
     const size_t rec_bytes = gb_align((size_t)records_cap * PK_REC_WORDS * 4);
     // ---- hit lists: ray-subset rounds ----
     const size_t list_bytes = gb_align((size_t)tasks_cap * 8);
-    char* w = (char*)gb_workspace(ctx, 4096 + rec_bytes + 2 * list_bytes);
+    char* w = (char*)gb_workspace(ctx, GB_WS_HEAD + rec_bytes + 2 * list_bytes);
     if (!w) return GRACE_B200_ENOMEM;
-    int* records = (int*)(w + 4096);
-    int2* lists[2] = { (int2*)(w + 4096 + rec_bytes), (int2*)(w + 4096 + rec_bytes + list_bytes) };
+    int* records = (int*)(w + GB_WS_HEAD);
+    int2* lists[2] = { (int2*)(w + GB_WS_HEAD + rec_bytes), (int2*)(w + GB_WS_HEAD + rec_bytes + list_bytes) };
     int* n_counts = ctx->d_scalars + GB_SC_TASKS;      // [0] records, [1] list 0, [2] list 1, [4,5] step sum (64-bit), [6] units done
     GB_CUDA(cudaMemsetAsync(n_counts, 0, 8 * sizeof(int), st));
     const int widths[3] = { 8, 2, 1 };
@@ -674,6 +698,63 @@ int launch_trace(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, size_t n_ray
     return GRACE_B200_OK;
 }
 
+} // namespace
+
+// One-pass hit lists, first half: the counting traversal also records every hit {integral, distance, index} in
+// chunk chains in the workspace (work stealing as for hit counts).  d_counts receives the per-ray counts.
+int gb_trace_record_f4(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, size_t n_rays, const float* d_spheres4, size_t n,
+                       const grace_b200_tree* tree, int* d_counts, cudaStream_t st)
+{
+    ctx->rec_valid = 0;
+    if (ctx->trace_mode != GRACE_B200_TRACE_PACKET || !ctx->one_pass_lists || tree->max_per_leaf > 128 || n_rays % 32 || n_rays == 0 ||
+        n_rays >= (1ull << 31))
+        return GRACE_B200_EINVAL;
+    (void)n;
+    const int n_packets = (int)(n_rays / 32);
+    int rc;
+    if (tree->max_per_leaf <= 32)
+        rc = launch_packet<MODE_REC, 32>(ctx, d_rays, n_packets, d_spheres4, tree, d_counts, nullptr, nullptr, nullptr, nullptr, nullptr, st, nullptr);
+    else if (tree->max_per_leaf <= 64)
+        rc = launch_packet<MODE_REC, 64>(ctx, d_rays, n_packets, d_spheres4, tree, d_counts, nullptr, nullptr, nullptr, nullptr, nullptr, st, nullptr);
+    else
+        rc = launch_packet<MODE_REC, 128>(ctx, d_rays, n_packets, d_spheres4, tree, d_counts, nullptr, nullptr, nullptr, nullptr, nullptr, st, nullptr);
+    if (rc) { ctx->rec_valid = 0; return rc; }
+    ctx->rec_rays = d_rays; ctx->rec_n_rays = n_rays; ctx->rec_offsets = d_counts;
+    ctx->rec_valid = tree->max_per_leaf <= 32 ? 32 : tree->max_per_leaf <= 64 ? 64 : 128;
+    return GRACE_B200_OK;
+}
+
+// Between the two halves, once the scan has turned the counts into offsets: the position of every stolen subtree's
+// first hit, per ray (rec_resolve_kernel).  A malformed theft tree raises the overflow flag = two passes.
+int gb_trace_resolve_recorded(grace_b200_ctx* ctx, const int* d_offsets, cudaStream_t st)
+{
+    if (!ctx->rec_valid) return GRACE_B200_OK;
+    PkArgs P; PkTasks T;
+    memcpy(&P, ctx->rec_blob, sizeof(PkArgs));
+    memcpy(&T, ctx->rec_blob + sizeof(PkArgs), sizeof(PkTasks));
+    const int blocks = std::min((P.n_packets + 3) / 4, ctx->sm_count * 16);
+    rec_resolve_kernel<<<blocks, 128, 0, st>>>(T.roots, (const int*)T.root_cum, T.records, d_offsets, P.n_packets,
+                                               T.lb + PK_LB_CREATED, T.records_cap, T.lb + PK_LB_OVERFLOW);
+    GB_LAUNCH_CHECK();
+    rec_order_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(T.pool, T.pool_ctr, T.pool_cap, T.roots, T.records, T.order);
+    GB_LAUNCH_CHECK();
+    return GRACE_B200_OK;
+}
+
+// Second half: copy the recorded hits to the caller's arrays, each ray's from its offset on, in emission order.
+int gb_trace_copy_recorded(grace_b200_ctx* ctx, const int* d_offsets, int* d_idx, float* d_integ, float* d_dist, cudaStream_t st)
+{
+    if (!ctx->rec_valid) return GRACE_B200_EINVAL;
+    ctx->rec_valid = 0;
+    PkArgs P; PkTasks T;
+    memcpy(&P, ctx->rec_blob, sizeof(PkArgs));
+    memcpy(&T, ctx->rec_blob + sizeof(PkArgs), sizeof(PkTasks));
+    rec_copy_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(T.pool, T.pool_ctr, T.pool_cap, T.order, T.records, d_offsets, d_idx, d_integ, d_dist);
+    GB_LAUNCH_CHECK();
+    return GRACE_B200_OK;
+}
+
+namespace {
 } // namespace
 
 extern "C" {
@@ -815,6 +896,12 @@ int grace_b200_trace_hits_fill_f4(grace_b200_ctx* ctx, const grace_b200_ray* d_r
 {
     GB_REQUIRE(d_ray_offsets && d_hit_indices && d_hit_integrals && d_hit_distances,
                GRACE_B200_EINVAL, "NULL argument");
+    // the count call that produced these offsets has recorded the hits themselves (one traversal instead of two),
+    // unless something else has used the workspace since or its hit pool ran dry
+    if (ctx && ctx->rec_valid && ctx->rec_rays == d_rays && ctx->rec_n_rays == n_rays && ctx->rec_offsets == d_ray_offsets &&
+        ctx->rec_epoch == ctx->ws_epoch)
+        return gb_trace_copy_recorded(ctx, d_ray_offsets, d_hit_indices, d_hit_integrals, d_hit_distances, (cudaStream_t)stream);
+    if (ctx) ctx->rec_valid = 0;
     return launch_trace<MODE_FILL>(ctx, d_rays, n_rays, d_spheres4, n, tree, nullptr, nullptr,
                                    d_ray_offsets, d_hit_indices, d_hit_integrals, d_hit_distances,
                                    (cudaStream_t)stream);

@@ -73,8 +73,8 @@ constexpr int PK_ROOM_MIN = PK_ROOM_MIN_V;   // flush when fewer than this many 
 
 template <int MODE, int M4>
 struct PkWarp {
-    static constexpr bool NEED_Q = (MODE == MODE_CUMULATIVE || MODE == MODE_FILL);
-    static constexpr bool NEED_I = (MODE == MODE_FILL);
+    static constexpr bool NEED_Q = (MODE == MODE_CUMULATIVE || MODE == MODE_FILL || MODE == MODE_REC);
+    static constexpr bool NEED_I = (MODE == MODE_FILL || MODE == MODE_REC);
     float4 prims[M4];                          // staged leaf {x,y,z,h*h} or {c-o, h*h}
     float4 rays[64];                           // ray r: {dx,dy,dz,ox} {oy,oz,len,-}
     float4 raw[PK_BATCH * M4];                 // cp.async landing zone
@@ -86,7 +86,8 @@ struct PkWarp {
     float2 q2[NEED_I ? PK_QD * 32 : 2];        // FIFO {distance, index bits}
     // term chain of a recording task (column densities, stolen subtrees): see pk_chain_append
     int ch_on, ch_cur, ch_head, ch_fail;       // recording?  current / first chunk, pool exhausted
-    int ch_off, ch_nb;                         // bytes and blocks used in the current chunk
+    int ch_off, ch_nb;                         // bytes and blocks used in the current chunk (hit records: entries used, -)
+    int ch_unit;                               // hit records: the unit the chunk belongs to (packet, or -1 - theft record)
     char* pool; int* pool_ctr; int pool_cap;
 };
 
@@ -130,6 +131,8 @@ __device__ __forceinline__ float pk_lerp(float b2, float ir, const double2* tabl
     return (float)__fma_rn((double)t, e.y, e.x);
 }
 
+#define NEED_I_(mode) ((mode) == MODE_FILL || (mode) == MODE_REC)     // hit lists: the FIFO also carries {distance, index}
+
 // Everything a packet accumulates per lane, plus where hit lists go.
 struct PkAcc {
     int count; float cum; int cursor;
@@ -162,7 +165,7 @@ __device__ __forceinline__ void pk_flush_eval(PkWarp<MODE, M4>& W, int qn, int l
         const float w = pk_lerp(e.x, e.y, table);
         const float ir2 = __fmul_rn(e.y, e.y);
         // per-hit value as stored (OnHit_sphere_individual): one FMUL
-        W.q[c] = MODE == MODE_FILL ? make_float2(__fmul_rn(w, ir2), 0.f) : make_float2(w, ir2);
+        W.q[c] = (MODE == MODE_FILL || MODE == MODE_REC) ? make_float2(__fmul_rn(w, ir2), 0.f) : make_float2(w, ir2);
     }
     __syncwarp();
 }
@@ -173,11 +176,12 @@ __device__ __forceinline__ void pk_flush_eval(PkWarp<MODE, M4>& W, int qn, int l
 template <int MODE, int M4>
 __device__ __noinline__ void pk_chain_append(PkWarp<MODE, M4>& W, int qn, int lane, unsigned lt)
 {
+    constexpr int EB = 8;                             // bytes per term {W, 1/h^2}
     const unsigned mask = __ballot_sync(0xffffffffu, qn > 0);
     if (mask == 0u) return;
     const int rows = __reduce_max_sync(0xffffffffu, qn);
     const int ncols = __popc(mask), rank = __popc(mask & lt);
-    const int size = 8 * rows * ncols;
+    const int size = EB * rows * ncols;
     int cur = W.ch_cur, off = W.ch_off, nb = W.ch_nb;
     if (cur < 0 || nb == PK_CH_NB || off + size > PK_CH_BYTES) {
         if (W.ch_fail) return;                   // pool exhausted earlier: the unit is about to abort
@@ -273,6 +277,92 @@ __device__ __noinline__ float pk_fold_chain(const char* pool, int head, float cu
     return cum;
 }
 
+// ---- one-pass hit lists (MODE_REC) ----
+// The counting traversal also records every hit, in chunks of PK_RCH_BYTES taken from a pool by atomic
+// ticket: a 32-byte header {entries, unit, which of the unit's chunks, -} and up to PK_RCH_CAP entries
+//     {integral, distance, primitive index, (k << 5) | lane}
+// where k says that this is the k-th hit of ray `lane` WITHIN THE UNIT (a packet, or a stolen subtree of
+// one).  Entries are self-describing, so a chunk can be copied to the caller's arrays by any warp once
+// the position of its unit's first hit is known for each ray (rec_resolve_kernel below); no chain has to
+// be walked.  A flush lists the occupied FIFO cells ray-major exactly like pk_flush_fill, so the copy's
+// stores land on a few contiguous stretches; it may straddle two chunks, nothing is padded.
+constexpr int PK_RCH_BYTES = 8192;
+constexpr int PK_RCH_CAP = (PK_RCH_BYTES - 32) / 16;
+constexpr int PK_RCH_MAXK = 1 << 26;          // hits of one ray within one unit that (k << 5 | lane) can hold
+
+template <int MODE, int M4>
+__device__ __noinline__ int pk_flush_rec(PkWarp<MODE, M4>& W, int qn, int count, int lane, const double2* table)
+{
+    __syncwarp();       // entries may have been written by other lanes (transposed leaves)
+    int incl = qn;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int first = incl - qn;
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return count;
+    if (W.ch_fail) return count + qn;             // pool exhausted earlier: the counts stay right, the lists are dropped
+    if (__any_sync(0xffffffffu, count + qn >= PK_RCH_MAXK)) { if (lane == 0) W.ch_fail = 1; __syncwarp(); return count + qn; }
+#pragma unroll
+    for (int j = 0; j < PK_QD; ++j)
+        if (j < qn) W.cells[first + j] = (unsigned char)(j * 32 + lane);
+    const int cur = W.ch_cur, used = W.ch_off;
+    const int room = cur >= 0 ? PK_RCH_CAP - used : 0;
+    int nxt = -1;
+    if (total > room) {
+        if (lane == 0) { nxt = atomicAdd(W.pool_ctr, 1); if (nxt >= W.pool_cap) nxt = -1; }
+        nxt = __shfl_sync(0xffffffffu, nxt, 0);
+        if (nxt < 0) { if (lane == 0) W.ch_fail = 1; __syncwarp(); return count + qn; }
+    }
+    __syncwarp();
+    // cell k goes to d0[k] while the current chunk has room, to d1[k] in the new one
+    float4* d0 = (float4*)(W.pool + (size_t)max(cur, 0) * PK_RCH_BYTES + 32) + used;
+    float4* d1 = (float4*)(W.pool + (size_t)max(nxt, 0) * PK_RCH_BYTES + 32) - room;
+    for (int base = 0; base < total; base += 32) {
+        const int k = base + lane;
+        const bool on = k < total;
+        const int c = on ? W.cells[k] : 0;
+        const int cnt = __shfl_sync(0xffffffffu, count, c & 31);      // the owning ray's hits so far
+        if (on) {
+            const float2 e = W.q[c], e2 = W.q2[c];
+            const float w = pk_lerp(e.x, e.y, table);
+            const float val = __fmul_rn(w, __fmul_rn(e.y, e.y));       // OnHit_sphere_individual: one FMUL
+            const int code = ((cnt + (c >> 5)) << 5) | (c & 31);
+            (k < room ? d0 : d1)[k] = make_float4(val, e2.x, e2.y, __int_as_float(code));
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        if (nxt >= 0) {
+            const int nb = W.ch_nb;
+            if (cur >= 0) *(int4*)(W.pool + (size_t)cur * PK_RCH_BYTES) = make_int4(PK_RCH_CAP, W.ch_unit, nb - 1, 0);     // full
+            W.ch_cur = nxt; W.ch_off = total - room; W.ch_nb = nb + 1;
+        } else W.ch_off = used + total;
+    }
+    __syncwarp();
+    return count + qn;
+}
+
+// The unit is finished: header of its last chunk.  Returns the first of the consecutive slots of the copy
+// order that the unit's chunks take (its k-th chunk is copied k-th of them, by the same or a neighbouring
+// warp at about the same time: a ray's hits of consecutive chunks are neighbours in the caller's arrays, and
+// the sectors they share are completed while still in L2).
+template <int MODE, int M4>
+__device__ __forceinline__ int pk_rec_close(PkWarp<MODE, M4>& W, int* slot_ctr, int lane)
+{
+    __syncwarp();
+    const int cur = W.ch_cur;
+    int start = 0;
+    if (cur >= 0 && lane == 0) {
+        const int nb = W.ch_nb;
+        *(int4*)(W.pool + (size_t)cur * PK_RCH_BYTES) = make_int4(W.ch_off, W.ch_unit, nb - 1, 0);
+        start = atomicAdd(slot_ctr, nb);
+    }
+    return start;      // lane 0's is the one
+}
+
 template <int MODE, int M4>
 __device__ __noinline__ float pk_flush_cum(PkWarp<MODE, M4>& W, int qn, float cum, int lane, unsigned lt, const double2* table)
 {
@@ -336,6 +426,9 @@ __device__ __forceinline__ void pk_flush(PkWarp<MODE, M4>& W, PkAcc& A, int lane
     if (MODE == MODE_CUMULATIVE) A.cum = pk_flush_cum<MODE, M4>(W, A.qn, A.cum, lane, lt, table);
     if (MODE == MODE_FILL)
         A.cursor = pk_flush_fill<MODE, M4>(W, A.qn, A.cursor, lane, lt, table, A.hit_idx, A.hit_integral, A.hit_dist);
+    if (MODE == MODE_REC) {       // one-pass hit lists: evaluate, count, record (positions are assigned later)
+        A.count = pk_flush_rec<MODE, M4>(W, A.qn, A.count, lane, table);
+    }
     A.qn = 0;
     A.room = PK_QD;
 }
@@ -503,12 +596,12 @@ __device__ __forceinline__ void pk_leaf_dense(PkWarp<MODE, M4>& W, int n_kept, c
             const bool hit1 = pk_test<COMMON>(s1, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, ray.length, b21, dot1) && lane_on;
             if (hit0) {
                 W.q[qn * 32 + lane] = make_float2(b20, W.ir[i]);
-                if (MODE == MODE_FILL) W.q2[qn * 32 + lane] = make_float2(dot0, __int_as_float(W.idx[i]));
+                if (NEED_I_(MODE)) W.q2[qn * 32 + lane] = make_float2(dot0, __int_as_float(W.idx[i]));
                 ++qn;
             }
             if (hit1) {
                 W.q[qn * 32 + lane] = make_float2(b21, W.ir[i + 1]);
-                if (MODE == MODE_FILL) W.q2[qn * 32 + lane] = make_float2(dot1, __int_as_float(W.idx[i + 1]));
+                if (NEED_I_(MODE)) W.q2[qn * 32 + lane] = make_float2(dot1, __int_as_float(W.idx[i + 1]));
                 ++qn;
             }
         }
@@ -518,7 +611,7 @@ __device__ __forceinline__ void pk_leaf_dense(PkWarp<MODE, M4>& W, int n_kept, c
             const bool hit = pk_test<COMMON>(s, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, ray.length, b2, dot) && lane_on;
             if (hit) {
                 W.q[qn * 32 + lane] = make_float2(b2, W.ir[i]);
-                if (MODE == MODE_FILL) W.q2[qn * 32 + lane] = make_float2(dot, __int_as_float(W.idx[i]));
+                if (NEED_I_(MODE)) W.q2[qn * 32 + lane] = make_float2(dot, __int_as_float(W.idx[i]));
                 ++qn;
             }
         }
@@ -540,7 +633,7 @@ __device__ __forceinline__ void pk_leaf_sparse(PkWarp<MODE, M4>& W, unsigned mas
         float ir = 0.f;
         int pidx = 0;
         if (MODE != MODE_COUNT && have) ir = W.ir[j];
-        if (MODE == MODE_FILL && have) pidx = W.idx[j];
+        if (NEED_I_(MODE) && have) pidx = W.idx[j];
         unsigned m = mask;
         while (m) {
             const int r = __ffs(m) - 1;
@@ -563,7 +656,7 @@ __device__ __forceinline__ void pk_leaf_sparse(PkWarp<MODE, M4>& W, unsigned mas
                     const int take = min(PK_QD - qn_r, nh - done);
                     if (hit && rank >= done && rank < done + take) {
                         W.q[(qn_r + rank - done) * 32 + r] = make_float2(b2, ir);
-                        if (MODE == MODE_FILL) W.q2[(qn_r + rank - done) * 32 + r] = make_float2(dot, __int_as_float(pidx));
+                        if (NEED_I_(MODE)) W.q2[(qn_r + rank - done) * 32 + r] = make_float2(dot, __int_as_float(pidx));
                     }
                     if (lane == r) A.qn += take;
                     qn_r += take;
@@ -624,7 +717,7 @@ constexpr int PK_ADV_AGE = PK_ADV_AGE_V;                     // steps after whic
 constexpr int PK_SPIN_LIMIT = 1 << 20;              // polls (up to ~4 us apart) before a waiting warp gives up (error 3)
 
 enum { PK_KIND_PACKETS = 0, PK_KIND_TASKS = 1, PK_KIND_FOLD = 2 };
-enum { PK_LB_FINISHED = 0, PK_LB_CREATED = 1 };     // units finished; tasks created (= theft records)
+enum { PK_LB_FINISHED = 0, PK_LB_CREATED = 1, PK_LB_OVERFLOW = 7 };     // units finished; tasks created (= theft records); hit pool ran dry
 
 struct PkTasks {
     int kind;
@@ -639,6 +732,7 @@ struct PkTasks {
     int* lb;                       // PK_LB_*
     char* pool; int* pool_ctr; int pool_cap;
     int2* roots; float* root_cum; int* n_roots;    // robbed packets: {packet, latest theft}, their own sums
+    int* order;                    // hit records: chunks in copy order
     // ---- ray-subset rounds (hit lists) ----
     const int2* tasks_in;     // PK_KIND_TASKS: {record, ray subset}
     const int* n_tasks_in;
@@ -850,7 +944,8 @@ trace_packet_kernel(const __grid_constant__ PkArgs P, const __grid_constant__ Pk
     using Warp = PkWarp<MODE, M4>;
     constexpr bool NEED_Q = Warp::NEED_Q;
     constexpr bool SUB = MODE != MODE_FILL;           // subtree donation; hit lists: ray-subset rounds
-    constexpr bool CHAIN = MODE == MODE_CUMULATIVE;   // ordered term chains + fold
+    constexpr bool CHAIN = MODE == MODE_CUMULATIVE || MODE == MODE_REC;   // ordered chains + fold / copy launch
+    constexpr bool REC = MODE == MODE_REC;            // hit lists in one traversal: EVERY unit records its hits
     extern __shared__ __align__(16) unsigned char pk_smem[];
     double2* s_table = (double2*)pk_smem;     // {T[i], T[i+1] - T[i]}
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -957,12 +1052,15 @@ trace_packet_kernel(const __grid_constant__ PkArgs P, const __grid_constant__ Pk
         int sp = 0;
         int top = root;                  // top of stack in a register; -1 = empty, <= -2 = FOLD entry
         unsigned top_mask = 0xffffffffu;
-        if (CHAIN && lane == 0) { W.ch_on = 0; W.ch_fail = 0; W.ch_cur = -1; W.ch_head = -1; }
+        if (CHAIN && lane == 0) {
+            W.ch_on = 0; W.ch_fail = 0; W.ch_cur = -1; W.ch_head = -1;
+            if (REC) { W.ch_off = 0; W.ch_nb = 0; W.ch_unit = my_task >= 0 ? -1 - my_task : packet; }
+        }
         if (SUB && my_task >= 0) {
             // stolen stack entries, for all rays of the unit they were taken from
             sp = __ldcg(rec + PK_DR_N);
             if (lane < sp) W.stack[lane] = __ldcg((const int2*)(rec + PK_DR_ENTRIES) + lane);
-            if (CHAIN && lane == 0) W.ch_on = 1;
+            if (CHAIN && !REC && lane == 0) W.ch_on = 1;
             __syncwarp();
             PK_POP();
         } else if (FOLD) {
@@ -993,7 +1091,7 @@ trace_packet_kernel(const __grid_constant__ PkArgs P, const __grid_constant__ Pk
         int next_check = T.budget, hold_until = 0;
         PK_DBG(unsigned long long dbg_recs = 0; const unsigned long long dbg_t0 = pk_now();)
         for (;;) {
-            if (CHAIN && W.ch_fail) { aborted = true; break; }      // the chunk pool ran dry
+            if (MODE == MODE_CUMULATIVE && W.ch_fail) { aborted = true; break; }      // the chunk pool ran dry
             // ---- every PK_CHECK_EVERY steps: publish progress, collect and answer a thief's request ----
             if (donating && guard0 - guard >= next_check) {
                 const int steps = guard0 - guard;
@@ -1160,7 +1258,7 @@ trace_packet_kernel(const __grid_constant__ PkArgs P, const __grid_constant__ Pk
                     if (keep) {
                         const int dst = n_kept + __popc(m & lt);
                         if (NEED_Q) W.ir[dst] = __fdiv_rn(1.0f, s.w);
-                        if (MODE == MODE_FILL) W.idx[dst] = first + i;
+                        if (NEED_I_(MODE)) W.idx[dst] = first + i;
                         s.w = __fmul_rn(s.w, s.w);
                         if (common) {
                             s.x = __fsub_rn(s.x, ray.ox); s.y = __fsub_rn(s.y, ray.oy); s.z = __fsub_rn(s.z, ray.oz);
@@ -1198,8 +1296,14 @@ trace_packet_kernel(const __grid_constant__ PkArgs P, const __grid_constant__ Pk
                 if (guard0 - guard >= PK_ADV_AGE && T.adv[me & (PK_ADV - 1)] == me + 1) T.adv[me & (PK_ADV - 1)] = 0;
             }
         }
+        if (REC && !FOLD && W.ch_fail && lane == 0) atomicExch(T.lb + PK_LB_OVERFLOW, 1);     // pool dry: counts are right, lists incomplete
         if (SUB && my_task >= 0) {           // a stolen subtree
-            if (CHAIN) {                     // publish its chain (or its failure) and what was stolen from it
+            if (REC) {                       // hit records: its own hits per ray (the stack entries are no longer needed) and its thefts
+                const int start = pk_rec_close<MODE, M4>(W, T.n_roots, lane);
+                int* r = T.records + (size_t)my_task * PK_DREC_WORDS;
+                r[PK_DR_ENTRIES + lane] = A.count;
+                if (lane == 0) { r[PK_DR_HEAD] = start; r[PK_DR_DONS] = don_head; r[PK_DR_STATUS] = 1; }
+            } else if (CHAIN) {              // publish its chain (or its failure) and what was stolen from it
                 if (W.ch_fail) aborted = true;
                 pk_chain_close<MODE, M4>(W, lane);
                 if (lane == 0) {
@@ -1207,10 +1311,14 @@ trace_packet_kernel(const __grid_constant__ PkArgs P, const __grid_constant__ Pk
                     r[PK_DR_HEAD] = W.ch_head; r[PK_DR_DONS] = don_head; r[PK_DR_STATUS] = aborted ? 2 : 1;
                 }
             }
-            if (MODE == MODE_COUNT && lane_on && A.count) atomicAdd(P.out_counts + ray_index, A.count);
+            if ((MODE == MODE_COUNT || REC) && lane_on && A.count) atomicAdd(P.out_counts + ray_index, A.count);
         } else if (SUB && don_head >= 0) {   // a robbed packet
-            if (MODE == MODE_COUNT && lane_on) atomicAdd(P.out_counts + ray_index, A.count);   // its tasks add to the same (zeroed) cell
-            if (CHAIN) {                     // its own sum goes to a root slot; the fold launch adds the rest
+            if ((MODE == MODE_COUNT || REC) && lane_on) atomicAdd(P.out_counts + ray_index, A.count);   // its tasks add to the same (zeroed) cell
+            if (REC) {                       // its own hits per ray and the thefts, for rec_resolve_kernel
+                const int start = pk_rec_close<MODE, M4>(W, T.n_roots, lane);
+                ((int*)T.root_cum)[ray_index] = A.count;
+                if (lane == 0) T.roots[packet] = make_int2(start, don_head);
+            } else if (CHAIN) {              // its own sum goes to a root slot; the fold launch adds the rest
                 int slot = 0;
                 if (lane == 0) slot = atomicAdd(T.n_roots, 1);
                 slot = __shfl_sync(0xffffffffu, slot, 0);
@@ -1218,8 +1326,12 @@ trace_packet_kernel(const __grid_constant__ PkArgs P, const __grid_constant__ Pk
                 if (lane == 0) T.roots[slot] = make_int2(packet, don_head);
             }
         } else {
-            if (MODE == MODE_COUNT && lane_on) P.out_counts[ray_index] = A.count;
+            if ((MODE == MODE_COUNT || REC) && lane_on) P.out_counts[ray_index] = A.count;
             if (MODE == MODE_CUMULATIVE && lane_on) P.out_cum[ray_index] = A.cum;
+            if (REC) {
+                const int start = pk_rec_close<MODE, M4>(W, T.n_roots, lane);
+                if (lane == 0) T.roots[packet] = make_int2(start, -1);
+            }
         }
         if (donating) {
             __threadfence();
@@ -1240,6 +1352,113 @@ trace_packet_kernel(const __grid_constant__ PkArgs P, const __grid_constant__ Pk
 #ifdef PK_PROF_LANES
             pp[1] = pf_l1; pp[2] = pf_l2; pp[3] = pf_l3;
 #endif
+        }
+    }
+}
+
+// ---- one-pass hit lists: where each unit's hits start, then the copy ----
+// Traversal order of a ray's hits: the unit's own, then what was stolen from it, latest theft first
+// (thefts take the BOTTOM of the stack, i.e. what the unit would have walked last), each stolen subtree
+// recursively the same.  So a pre-order walk of a packet's theft tree with a running per-ray position
+// gives every task the position of its first hit; it is stored in the second half of the task's record
+// (the first half holds its own hit count per ray).  One warp per robbed packet, lane = ray.
+constexpr int PK_RESOLVE_DEPTH = 128;
+__global__ void __launch_bounds__(128) rec_resolve_kernel(const int2* __restrict__ roots, const int* __restrict__ root_own,
+                                                         int* records, const int* __restrict__ offsets, int n_packets,
+                                                         const int* __restrict__ created_ptr, int records_cap, int* overflow)
+{
+    const int created = min(__ldg(created_ptr), records_cap);
+    __shared__ int stk[4][PK_RESOLVE_DEPTH];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int packet = blockIdx.x * 4 + w; packet < n_packets; packet += gridDim.x * 4) {
+        int node = __ldg(&roots[packet].y);
+        if (node < 0) continue;
+        int cur = __ldg(offsets + packet * 32 + lane) + __ldg(root_own + packet * 32 + lane);
+        int sp = 0;
+        for (int guard = 0;; ++guard) {
+            if (node < 0) {
+                if (sp == 0) break;
+                node = stk[w][--sp];
+            }
+            if (node >= created || guard > created) { if (lane == 0) atomicExch(overflow, 1); break; }     // malformed: two passes
+            int* rec = records + (size_t)node * PK_DREC_WORDS;
+            const int older = __ldcg(rec + PK_DR_OLDER), dons = __ldcg(rec + PK_DR_DONS), status = __ldcg(rec + PK_DR_STATUS);
+            const int own = __ldcg(rec + PK_DR_ENTRIES + lane);
+            if (status != 1) { if (lane == 0) atomicExch(overflow, 1); break; }
+            rec[PK_DR_ENTRIES + 32 + lane] = cur;
+            cur += own;
+            if (older >= 0) {
+                if (sp >= PK_RESOLVE_DEPTH) { if (lane == 0) atomicExch(overflow, 1); break; }
+                __syncwarp();
+                if (lane == 0) stk[w][sp] = older;
+                ++sp;
+                __syncwarp();
+            }
+            node = dons;
+        }
+        __syncwarp();
+    }
+}
+
+// Copy order: chunk -> its slot (first slot of its unit + which of the unit's chunks it is).
+__global__ void __launch_bounds__(256) rec_order_kernel(const char* __restrict__ pool, const int* __restrict__ pool_ctr, int pool_cap,
+                                                       const int2* __restrict__ roots, const int* __restrict__ records,
+                                                       int* __restrict__ order)
+{
+    const int n_chunks = min(__ldg(pool_ctr), pool_cap);
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_chunks; c += gridDim.x * blockDim.x) {
+        const int4 h = __ldg((const int4*)(pool + (size_t)c * PK_RCH_BYTES));     // entries, unit, which, -
+        const int start = h.y >= 0 ? __ldg(&roots[h.y].x) : __ldg(records + (size_t)(-1 - h.y) * PK_DREC_WORDS + PK_DR_HEAD);
+        const int slot = start + h.z;
+        if (slot >= 0 && slot < n_chunks) order[slot] = c;
+    }
+}
+
+// Entry {integral, distance, index, k << 5 | lane} goes to position (first hit of the chunk's unit for ray
+// `lane`) + k of the caller's arrays.  A warp copies PK_COPY_G chunks that are neighbours in the copy order.
+constexpr int PK_COPY_G = 4;
+__global__ void __launch_bounds__(256) rec_copy_kernel(const char* __restrict__ pool, const int* __restrict__ pool_ctr, int pool_cap,
+                                                      const int* __restrict__ order, const int* __restrict__ records,
+                                                      const int* __restrict__ offsets,
+                                                      int* __restrict__ hit_idx, float* __restrict__ hit_integral, float* __restrict__ hit_dist)
+{
+    const int lane = threadIdx.x & 31;
+    const int n_chunks = min(__ldg(pool_ctr), pool_cap);
+    const int n_warps = gridDim.x * (blockDim.x >> 5);
+    const int n_groups = (n_chunks + PK_COPY_G - 1) / PK_COPY_G;
+    for (int grp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); grp < n_groups; grp += n_warps) {
+        int my_chunk = -1;
+        if (lane < PK_COPY_G && grp * PK_COPY_G + lane < n_chunks) my_chunk = __ldg(order + grp * PK_COPY_G + lane);
+        int2 my_h = make_int2(0, 0);
+        if (my_chunk >= 0) my_h = __ldg((const int2*)(pool + (size_t)my_chunk * PK_RCH_BYTES));
+#pragma unroll 1
+        for (int g = 0; g < PK_COPY_G; ++g) {
+            const int chunk = __shfl_sync(0xffffffffu, my_chunk, g);
+            if (chunk < 0) break;
+            const int2 h = make_int2(__shfl_sync(0xffffffffu, my_h.x, g), __shfl_sync(0xffffffffu, my_h.y, g));         // entries, unit
+            const char* ch = pool + (size_t)chunk * PK_RCH_BYTES;
+            const int base = h.y >= 0 ? __ldg(offsets + (size_t)h.y * 32 + lane)
+                                      : __ldg(records + (size_t)(-1 - h.y) * PK_DREC_WORDS + PK_DR_ENTRIES + 32 + lane);
+            const float4* e = (const float4*)(ch + 32);
+            const int n = min(h.x, PK_RCH_CAP);
+            for (int k0 = 0; k0 < n; k0 += 256) {
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int k = k0 + u * 32 + lane;
+                    v[u] = k < n ? __ldcs(e + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int k = k0 + u * 32 + lane;
+                    const int code = __float_as_int(v[u].w);
+                    const int b = __shfl_sync(0xffffffffu, base, code & 31);
+                    if (k < n) {
+                        const int pos = b + (int)((unsigned)code >> 5);
+                        hit_integral[pos] = v[u].x; hit_dist[pos] = v[u].y; hit_idx[pos] = __float_as_int(v[u].z);
+                    }
+                }
+            }
         }
     }
 }

@@ -215,7 +215,9 @@ int grace_b200_set_trace_mode(grace_b200_ctx* ctx, int mode);
  * not unclaimed work is left (used by the tests to force splits). */
 #define GRACE_B200_BUDGET_EAGER (1 << 30)
 int grace_b200_set_trace_budget(grace_b200_ctx* ctx, int steps);
-/* Bytes of workspace for the per-hit terms {W, 1/h^2} that column-density tasks record for the
+/* (Also the pool in which grace_b200_trace_hits_count_f4 records the hits themselves, 16 bytes each, so that
+ * grace_b200_trace_hits_fill_f4 needs no second traversal; default there: 32 KiB per ray, 256 MiB to 4 GiB.)
+ * Bytes of workspace for the per-hit terms {W, 1/h^2} that column-density tasks record for the
  * ordered final sum; 0 (default) sizes it from the ray count (64 KiB per ray, 64 MiB to 2 GiB).
  * A pool that runs dry costs time, not correctness: the affected subtrees are walked again by the
  * launch that adds the terms up. */
@@ -251,7 +253,11 @@ int grace_b200_trace_cumulative_f4(grace_b200_ctx* ctx, const grace_b200_ray* d_
  *            with_sentinels != 0 each offset is shifted by its ray index and the
  *            total includes one sentinel slot per ray (trace_sph.cuh:196-207).
  *   _fill  : pass 2 writes (sphere index, kernel integral, distance) per hit in
- *            emission order starting at d_ray_offsets[ray].
+ *            emission order starting at d_ray_offsets[ray].  When it directly follows the
+ *            _count call for the same rays and offsets array (no other call on the context in
+ *            between) it is a copy: _count has recorded the hits in the workspace while it
+ *            counted them, so the tree is walked once, not twice as in the reference
+ *            (cuda/trace_sph.cuh:125-165).  Otherwise it walks the tree again.
  * Returns GRACE_B200_ERANGE if the total exceeds INT32_MAX (the reference's
  * offsets are int, trace_sph.cuh:117,137): tile the rays. */
 int grace_b200_trace_hits_count_f4(grace_b200_ctx* ctx, const grace_b200_ray* d_rays,

@@ -10,6 +10,9 @@ tree = gb.Tree(n, 32); gb.build_tree(s, tree)
 lo, hi = gb.min_max_x(s); c = (lo + hi) / 2
 lrs = [int(a) for a in sys.argv[1].split(",")] if len(sys.argv) > 1 else [23, 20, 17, 15, 12]
 tag = sys.argv[2] if len(sys.argv) > 2 else os.environ.get("GRACE_B200_LIB", "default")
+if os.environ.get("AB_BUDGET"):
+    gb.set_trace_budget(int(os.environ["AB_BUDGET"]))
+    tag += "_b" + os.environ["AB_BUDGET"]
 
 
 def timeit(fn, reps=5):
