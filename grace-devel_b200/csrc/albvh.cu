@@ -31,6 +31,7 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace {
 
@@ -273,6 +274,164 @@ leaves_kernel(const T* __restrict__ deltas_shifted, int n, int mpl,
                 node_flags[g] = 0u;
                 ++g;
             }
+        }
+    }
+}
+
+// max_per_leaf == W: leaves from a sliding-window argmax, no per-node scans at all.
+//
+// Call a node "big" when its subtree holds more than W primitives.  The leaves are exactly the
+// stretches between consecutive big nodes (a leaf [l, k] ends at the big node k that is its parent or
+// its parent's ... -- every node strictly inside is small, and so is the stretch's own root, whose
+// range is the whole stretch), with virtual big nodes at -1 and n - 1.  And node k is big iff the
+// interval around k on which delta(k) is the maximum -- left neighbours strictly smaller, right
+// neighbours smaller or equal, the tie rule of the reference -- spans more than W primitives, i.e. iff
+// k is the LEFTMOST maximum of some window of W consecutive deltas inside [0, n - 2].  Sliding-window
+// maxima cost O(1) per element (van Herk / Gil-Werman): with the deltas cut into blocks of W, the
+// window starting at element i of block b is the suffix [i, W) of block b + the prefix [0, i) of block
+// b + 1, so one thread owning a block's suffix maxima and the next block's prefix maxima marks the
+// argmax of W windows with ~14 instructions per node, all in registers (the table descent of
+// leaves_kernel took ~300 and was issue-bound at 3 % of the DRAM bandwidth).
+//
+// Thread t of a CTA works on the windows starting in block B0 - 2 + t; the marks falling into the next
+// block reach its owner through shared memory, so blocks B0 - 1 .. B0 + 253 have complete masks and
+// the CTA emits the leaves ending in blocks B0 .. B0 + 253 (the block before supplies "previous big
+// node").  Compaction, look-back and output are those of leaves_kernel.
+constexpr int LW_OWNED = LV_THREADS - 2;      // blocks of W nodes a CTA emits
+
+template <typename T, int W>
+__global__ void __launch_bounds__(LV_THREADS)
+leaves_window_kernel(const T* __restrict__ deltas_shifted, int n,
+                     int4* __restrict__ leaves, T* __restrict__ leaf_deltas_shifted,
+                     unsigned* __restrict__ node_flags, unsigned long long* __restrict__ block_state,
+                     unsigned* __restrict__ ticket, int* __restrict__ n_leaves_out, int n_tiles)
+{
+    extern __shared__ __align__(16) unsigned char lw_smem[];
+    T* win = (T*)lw_smem;                         // (LV_THREADS + 1) blocks, stride W + 1
+    __shared__ unsigned s_next[LV_THREADS];       // marks a thread's windows left in the following block
+    __shared__ unsigned s_mask[LV_THREADS];       // complete mask of the thread's block
+    __shared__ unsigned s_bid;
+    __shared__ unsigned s_warp_tot[LV_THREADS / 32];
+    __shared__ unsigned long long s_excl;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_bid = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const unsigned bid = s_bid;
+    const long long first_block = (long long)bid * LW_OWNED - 2;       // thread 0's block
+    // stage deltas of positions [first_block * W, (first_block + LV_THREADS + 1) * W): coalesced, clamped
+    {
+        const long long p0 = first_block * W;
+        for (int i = tid; i < (LV_THREADS + 1) * W; i += LV_THREADS) {
+            long long k = p0 + i;
+            k = k < -1 ? -1 : (k > n - 1 ? n - 1 : k);
+            win[(i / W) * (W + 1) + (i % W)] = __ldg(deltas_shifted + k + 1);
+        }
+    }
+    __syncthreads();
+    const long long blk = first_block + tid;      // this thread's block; its positions are blk * W + [0, W)
+    const T* mine = win + tid * (W + 1);
+    const T* next = mine + (W + 1);
+    // prefix maxima of the next block (value + leftmost position, as a mask of strict records)
+    T pv[W];
+    unsigned rec = 1u;
+    pv[0] = next[0];
+#pragma unroll
+    for (int i = 1; i < W; ++i) {
+        const T v = next[i];
+        const bool up = pv[i - 1] < v;
+        pv[i] = up ? v : pv[i - 1];
+        rec |= up ? (1u << i) : 0u;
+    }
+    // windows by descending start: running suffix maximum of this block (leftmost on ties)
+    unsigned A = 0u, Bn = 0u;
+    {
+        const long long s_max = (long long)n - 1 - W;          // last valid window start
+        T sv = mine[W - 1];
+        int si = W - 1;
+#pragma unroll
+        for (int i = W - 1; i >= 0; --i) {
+            if (i < W - 1) {
+                const T v = mine[i];
+                if (!(v < sv)) { sv = v; si = i; }
+            }
+            const long long s = blk * W + i;
+            if (s >= 0 && s <= s_max) {
+                if (i == 0 || !(sv < pv[i > 0 ? i - 1 : 0])) A |= 1u << si;
+                else Bn |= 1u << (31 - __clz(rec & ((1u << i) - 1u)));
+            }
+        }
+    }
+    s_next[tid] = Bn;
+    __syncthreads();
+    unsigned M = A | (tid > 0 ? s_next[tid - 1] : 0u);
+    // virtual big node at n - 1 (end of the last leaf)
+    if ((long long)(n - 1) >= blk * W && (long long)(n - 1) < (blk + 1) * W) M |= 1u << (int)((n - 1) - blk * W);
+    s_mask[tid] = M;
+    __syncthreads();
+    const bool owner = tid >= 2 && blk * W <= (long long)(n - 1);
+    const unsigned emit = owner ? __popc(M) : 0u;
+    unsigned incl = emit;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp_tot[warp] = incl;
+    __syncthreads();
+    unsigned add = 0, block_total = 0;
+#pragma unroll
+    for (int w = 0; w < LV_THREADS / 32; ++w) {
+        if (w < warp) add += s_warp_tot[w];
+        block_total += s_warp_tot[w];
+    }
+    const unsigned local_excl = add + incl - emit;
+    if (warp == 0) {
+        unsigned long long excl = 0;
+        if (bid == 0) {
+            if (lane == 0) gb_st_volatile_u64(block_state, (unsigned long long)block_total | ST_INCL);
+        } else {
+            if (lane == 0) gb_st_volatile_u64(block_state + bid, (unsigned long long)block_total | ST_AGG);
+            int t = (int)bid - 1;           // nearest predecessor not yet accounted for
+            for (;;) {
+                const int idx = t - lane;
+                unsigned long long v = ST_INCL;      // tiles before the first contribute 0
+                if (idx >= 0) {
+                    do { v = gb_ld_volatile_u64(block_state + idx); } while ((v & ST_MASK) == 0);
+                }
+                const unsigned im = __ballot_sync(0xffffffffu, (v & ST_MASK) == ST_INCL);
+                const int first = im ? __ffs(im) - 1 : 32;       // nearest tile with an inclusive prefix
+                unsigned long long cc = lane <= first ? (v & ~ST_MASK) : 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) cc += __shfl_xor_sync(0xffffffffu, cc, o);
+                excl += cc;
+                if (im) break;
+                t -= 32;
+            }
+            if (lane == 0) gb_st_volatile_u64(block_state + bid, (excl + block_total) | ST_INCL);
+        }
+        if (lane == 0) {
+            s_excl = excl;
+            if ((int)bid == n_tiles - 1) *n_leaves_out = (int)(excl + block_total);
+            if (bid == 0) leaf_deltas_shifted[0] = deltas_shifted[0];
+        }
+    }
+    __syncthreads();
+    if (emit) {
+        unsigned g = (unsigned)s_excl + local_excl;
+        // the big node before this block's first: in the previous block (a leaf holds at most W primitives), or -1
+        const unsigned pm = s_mask[tid - 1];
+        long long prev = pm ? (blk - 1) * W + (31 - __clz(pm)) : -1;
+        unsigned m = M;
+        while (m) {
+            const int bit = __ffs(m) - 1;
+            m &= m - 1;
+            const long long k = blk * W + bit;
+            leaves[g] = make_int4((int)(prev + 1), (int)(k - prev), 0, 0);
+            leaf_deltas_shifted[g + 1] = mine[bit];         // delta after the leaf's last primitive
+            node_flags[g] = 0u;
+            prev = k;
+            ++g;
         }
     }
 }
@@ -523,7 +682,17 @@ int leaves_stage(grace_b200_ctx* ctx, size_t n, const T* d_deltas, int mpl, int4
         return GRACE_B200_OK;
     };
     int lrc;
-    if (K <= 6 && sizeof(T) * 6 * level_words <= 112 * 1024) lrc = launch(leaves_kernel<T, true, 6>, sizeof(T) * 6 * level_words);
+    static const bool table_only = getenv("GRACE_B200_LEAVES_TABLE") != nullptr;      // A/B switch: the shared-memory table path
+    if (mpl == 32 && !table_only) {
+        const int n_blocks = ((int)n + 31) / 32;              // positions 0 .. n - 1
+        const int n_tiles = (n_blocks + LW_OWNED - 1) / LW_OWNED;          // <= lv_blocks: block_state is large enough
+        const size_t smem = sizeof(T) * (LV_THREADS + 1) * 33;
+        auto kernel = leaves_window_kernel<T, 32>;
+        GB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kernel<<<n_tiles, LV_THREADS, smem, st>>>(d_deltas, (int)n, d_leaves, w.leaf_deltas, w.flags, w.block_state, ticket,
+                                                  d_nleaves, n_tiles);
+        lrc = GRACE_B200_OK;
+    } else if (K <= 6 && sizeof(T) * 6 * level_words <= 112 * 1024) lrc = launch(leaves_kernel<T, true, 6>, sizeof(T) * 6 * level_words);
     else if (K <= 8 && sizeof(T) * 8 * level_words <= 112 * 1024) lrc = launch(leaves_kernel<T, true, 8>, sizeof(T) * 8 * level_words);
     else if (mpl <= 2048) lrc = launch(leaves_kernel<T, true, 0>, sizeof(T) * level_words);
     else lrc = launch(leaves_kernel<T, false, 0>, 0);
