@@ -500,94 +500,106 @@ __device__ __forceinline__ void nd_merge_rounds(NdSub<T>& S, bool& active, int l
 
 // FROM_AABB: `spheres` holds two float4 per primitive, {bx,by,bz,-} {tx,ty,tz,-}: boxes a user's
 // AABB functor produced (generic primitives), instead of {x,y,z,h} spheres.
+//
+// Warps are independent (no block barrier: with the block-wide stage the kernel spent its time waiting
+// for the one warp that merged the block's leftovers and for the lanes climbing with atomics): a warp
+// takes a ticket for ND_ROWS x 32 consecutive leaves, folds and merges them row by row, collects what
+// is left in its own shared-memory buffer, merges that, and climbs with the rest.
+constexpr int ND_ROWS = 4;
+constexpr int ND_GROUP = 32 * ND_ROWS;
+
 template <typename T, bool FROM_AABB>
 __global__ void __launch_bounds__(ND_THREADS)
 nodes_kernel(const float4* __restrict__ spheres, const int4* __restrict__ leaves,
              const int* __restrict__ n_leaves_ptr, const T* __restrict__ ld_shifted,
-             int4* nodes, unsigned* flags, int* __restrict__ root)
+             int4* nodes, unsigned* flags, int* __restrict__ root, int* __restrict__ ticket)
 {
-    __shared__ NdSub<T> s_sub[ND_THREADS];
-    __shared__ int s_cnt[ND_WARPS];
-    __shared__ int s_m;
+    extern __shared__ __align__(16) unsigned char nd_smem[];
     const int L = *n_leaves_ptr;
     const int n_nodes = L - 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // the block's window: ND_THREADS consecutive leaves, 32 per warp (block-uniform loop: barriers inside)
-    for (int B = blockIdx.x * ND_THREADS; B < L; B += gridDim.x * ND_THREADS) {
-    const int w = B + warp * 32;
-    const int leaf = w + lane;
-    bool active = leaf < L;
-
-    // ---- (1) leaf boxes ----
-    int2 lf = make_int2(0, 0);
-    if (active) lf = __ldg((const int2*)(leaves + leaf));
-    NdSub<T> S;
-    S.bx = S.by = S.bz = CUDART_INF_F;
-    S.tx = S.ty = S.tz = -CUDART_INF_F;
-    // every lane folds its own leaf: the loads of one lane are independent (deep unrolling keeps
-    // several 16-byte loads in flight) and the warp's leaves are contiguous in memory, so all
-    // the lines it touches are consumed in full
-#pragma unroll 4
-    for (int i = 0; i < lf.y; ++i) {
-        if (FROM_AABB) {
-            const float4 b = __ldg(spheres + 2 * (size_t)(lf.x + i)), t = __ldg(spheres + 2 * (size_t)(lf.x + i) + 1);
-            S.bx = fminf(S.bx, b.x); S.by = fminf(S.by, b.y); S.bz = fminf(S.bz, b.z);
-            S.tx = fmaxf(S.tx, t.x); S.ty = fmaxf(S.ty, t.y); S.tz = fmaxf(S.tz, t.z);
-        } else {
-            const float4 s = __ldg(spheres + lf.x + i);
-            // AABBSphere, generic/functors/aabb.h:9-26: centre -/+ h, one FADD each
-            S.bx = fminf(S.bx, __fsub_rn(s.x, s.w)); S.tx = fmaxf(S.tx, __fadd_rn(s.x, s.w));
-            S.by = fminf(S.by, __fsub_rn(s.y, s.w)); S.ty = fmaxf(S.ty, __fadd_rn(s.y, s.w));
-            S.bz = fminf(S.bz, __fsub_rn(s.z, s.w)); S.tz = fmaxf(S.tz, __fadd_rn(s.z, s.w));
-        }
-    }
-
-    // ---- (2a) the warp's 32 leaves ----
-    S.l = S.r = leaf;
-    S.cur = leaf + n_nodes;            // child index >= n_nodes marks a leaf
-    S.dl = ld_shifted[min(leaf, L)];            // delta(leaf - 1)
-    S.dr = ld_shifted[min(leaf + 1, L)];        // delta(leaf)
-    nd_merge_rounds<T>(S, active, lane, nodes);
-
-    // ---- (2b) what the block's warps have left, in order, through shared memory ----
-    const unsigned amask = __ballot_sync(0xffffffffu, active);
-    if (lane == 0) s_cnt[warp] = __popc(amask);
-    __syncthreads();
-    int base = 0, m = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    NdSub<T>* buf = (NdSub<T>*)nd_smem + warp * ND_GROUP;
+    const int n_groups = (L + ND_GROUP - 1) / ND_GROUP;
+    for (;;) {
+    int grp = 0;
+    if (lane == 0) grp = atomicAdd(ticket, 1);
+    grp = __shfl_sync(0xffffffffu, grp, 0);
+    if (grp >= n_groups) break;
+    const int G = grp * ND_GROUP;
+    // the leaf records of all rows are requested first
+    int2 lfs[ND_ROWS];
 #pragma unroll
-    for (int k = 0; k < ND_WARPS; ++k) { if (k < warp) base += s_cnt[k]; m += s_cnt[k]; }
-    if (active) s_sub[base + __popc(amask & ((1u << lane) - 1u))] = S;
-    __syncthreads();
-    if (warp == 0) {
-        // sweeps over windows of 32 subtrees; survivors are compacted to the front.  A pair
-        // straddling a window boundary may stay unmerged: stage (3) takes whatever is left.
-        int count = m;
-        for (int sweep = 0; sweep < 4 && count > 1; ++sweep) {
-            int out = 0;
-            bool merged_any = false;
-            for (int wb = 0; wb < count; wb += 32) {
-                bool act = wb + lane < count;
-                NdSub<T> X = s_sub[min(wb + lane, ND_THREADS - 1)];
-                const int before = __popc(__ballot_sync(0xffffffffu, act));
-                nd_merge_rounds<T>(X, act, lane, nodes);
-                const unsigned am = __ballot_sync(0xffffffffu, act);
-                merged_any |= __popc(am) != before;
-                __syncwarp();
-                if (act) s_sub[out + __popc(am & ((1u << lane) - 1u))] = X;     // out <= wb: never ahead of the reads
-                out += __popc(am);
-                __syncwarp();
-            }
-            count = out;
-            if (!merged_any) break;
-        }
-        if (lane == 0) s_m = count;
+    for (int row = 0; row < ND_ROWS; ++row) {
+        const int leaf = G + row * 32 + lane;
+        lfs[row] = leaf < L ? __ldg((const int2*)(leaves + leaf)) : make_int2(0, 0);
     }
-    __syncthreads();
-    m = s_m;
-
-    // ---- (3) climb across blocks ----
-    active = (int)threadIdx.x < m;
-    if (active) S = s_sub[threadIdx.x];
+    int count = 0;
+#pragma unroll 1
+    for (int row = 0; row < ND_ROWS; ++row) {
+        const int leaf = G + row * 32 + lane;
+        bool active = leaf < L;
+        if (!__any_sync(0xffffffffu, active)) break;
+        // ---- (1) leaf boxes ----
+        int2 lf = lfs[0];
+#pragma unroll
+        for (int k = 1; k < ND_ROWS; ++k) if (row == k) lf = lfs[k];
+        NdSub<T> S;
+        S.bx = S.by = S.bz = CUDART_INF_F;
+        S.tx = S.ty = S.tz = -CUDART_INF_F;
+        // every lane folds its own leaf: the loads of one lane are independent (deep unrolling keeps
+        // several 16-byte loads in flight) and the warp's leaves are contiguous in memory, so all
+        // the lines it touches are consumed in full
+#pragma unroll 8
+        for (int i = 0; i < lf.y; ++i) {
+            if (FROM_AABB) {
+                const float4 b = __ldg(spheres + 2 * (size_t)(lf.x + i)), t = __ldg(spheres + 2 * (size_t)(lf.x + i) + 1);
+                S.bx = fminf(S.bx, b.x); S.by = fminf(S.by, b.y); S.bz = fminf(S.bz, b.z);
+                S.tx = fmaxf(S.tx, t.x); S.ty = fmaxf(S.ty, t.y); S.tz = fmaxf(S.tz, t.z);
+            } else {
+                const float4 s = __ldg(spheres + lf.x + i);
+                // AABBSphere, generic/functors/aabb.h:9-26: centre -/+ h, one FADD each
+                S.bx = fminf(S.bx, __fsub_rn(s.x, s.w)); S.tx = fmaxf(S.tx, __fadd_rn(s.x, s.w));
+                S.by = fminf(S.by, __fsub_rn(s.y, s.w)); S.ty = fmaxf(S.ty, __fadd_rn(s.y, s.w));
+                S.bz = fminf(S.bz, __fsub_rn(s.z, s.w)); S.tz = fmaxf(S.tz, __fadd_rn(s.z, s.w));
+            }
+        }
+        // ---- (2a) the row's 32 leaves ----
+        S.l = S.r = leaf;
+        S.cur = leaf + n_nodes;            // child index >= n_nodes marks a leaf
+        S.dl = ld_shifted[min(leaf, L)];            // delta(leaf - 1)
+        S.dr = ld_shifted[min(leaf + 1, L)];        // delta(leaf)
+        nd_merge_rounds<T>(S, active, lane, nodes);
+        const unsigned amask = __ballot_sync(0xffffffffu, active);
+        if (active) buf[count + __popc(amask & lt)] = S;
+        count += __popc(amask);
+        __syncwarp();
+    }
+    // ---- (2b) what the rows have left, in order ----
+    // sweeps over windows of 32 subtrees; survivors are compacted to the front.  A pair straddling a
+    // window boundary may stay unmerged: stage (3) takes whatever is left.
+    for (int sweep = 0; sweep < 4 && count > 1; ++sweep) {
+        int out = 0;
+        bool merged_any = false;
+        for (int wb = 0; wb < count; wb += 32) {
+            bool act = wb + lane < count;
+            NdSub<T> X = buf[min(wb + lane, ND_GROUP - 1)];
+            const int before = __popc(__ballot_sync(0xffffffffu, act));
+            nd_merge_rounds<T>(X, act, lane, nodes);
+            const unsigned am = __ballot_sync(0xffffffffu, act);
+            merged_any |= __popc(am) != before;
+            __syncwarp();
+            if (act) buf[out + __popc(am & lt)] = X;     // out <= wb: never ahead of the reads
+            out += __popc(am);
+            __syncwarp();
+        }
+        count = out;
+        if (!merged_any) break;
+    }
+    // ---- (3) climb across warps ----
+    for (int cb = 0; cb < count; cb += 32) {
+    bool active = cb + lane < count;
+    NdSub<T> S = buf[min(cb + lane, ND_GROUP - 1)];
     int cur = S.cur, l = S.l, r = S.r;
     float bx = S.bx, by = S.by, bz = S.bz, tx = S.tx, ty = S.ty, tz = S.tz;
     bool right_child = active && S.dl < S.dr;
@@ -626,7 +638,8 @@ nodes_kernel(const float4* __restrict__ spheres, const int4* __restrict__ leaves
         right_child = dl < dr;
         parent = right_child ? l - 1 : r;
     }
-    __syncthreads();       // s_sub is reused by the next window
+    }
+    __syncwarp();       // the buffer is reused by the next group
     }
 }
 
@@ -706,12 +719,21 @@ template <typename T>
 int nodes_stage(grace_b200_ctx* ctx, const float4* d_prims, bool from_aabb, size_t cap, const int4* d_leaves,
                 const int* d_nleaves, const T* leaf_deltas, unsigned* flags, int4* d_nodes, int* d_root, cudaStream_t st)
 {
-    // warps stride over 32-leaf windows
-    const int nd_blocks = grid_cap(ctx, cap, ND_THREADS, 8);
-    if (from_aabb)
-        nodes_kernel<T, true><<<nd_blocks, ND_THREADS, 0, st>>>(d_prims, d_leaves, d_nleaves, leaf_deltas, d_nodes, flags, d_root);
-    else
-        nodes_kernel<T, false><<<nd_blocks, ND_THREADS, 0, st>>>(d_prims, d_leaves, d_nleaves, leaf_deltas, d_nodes, flags, d_root);
+    // warps take tickets for ND_GROUP-leaf groups; the grid is what the SMs can hold
+    int* nd_ticket = ctx->d_scalars + GB_SC_TICKET2;
+    GB_CUDA(cudaMemsetAsync(nd_ticket, 0, sizeof(int), st));
+    const size_t smem = (size_t)ND_WARPS * ND_GROUP * sizeof(NdSub<T>);
+    auto launch = [&](auto kernel) -> int {
+        GB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, ND_THREADS, smem));
+        const int need = (int)std::min<size_t>((cap + (size_t)ND_WARPS * ND_GROUP - 1) / ((size_t)ND_WARPS * ND_GROUP), 1u << 30);
+        const int nd_blocks = std::max(1, std::min(need, ctx->sm_count * std::max(per_sm, 1)));
+        kernel<<<nd_blocks, ND_THREADS, smem, st>>>(d_prims, d_leaves, d_nleaves, leaf_deltas, d_nodes, flags, d_root, nd_ticket);
+        return GRACE_B200_OK;
+    };
+    int lrc = from_aabb ? launch(nodes_kernel<T, true>) : launch(nodes_kernel<T, false>);
+    if (lrc) return lrc;
     GB_LAUNCH_CHECK();
     return GRACE_B200_OK;
 }

@@ -3,8 +3,8 @@
 // Replaces morton_keys30_sort_sph / morton_keys63_sort_sph (GRACE cuda/build_sph.cuh:41-82):
 // there, a temporary key vector is allocated per call, bounds cost two Thrust reductions
 // with host read-backs, and thrust::sort_by_key moves the 16-byte spheres through every
-// radix pass.  Here: bounds (optional) -> keys -> onesweep on (key, index) -> one gather
-// of the spheres, all on the caller's stream with no host synchronisation.
+// radix pass.  Here: bounds (optional) -> keys -> onesweep on (key, index), the last pass
+// gathering the spheres, all on the caller's stream with no host synchronisation.
 #include "common.cuh"
 #include "radix_sort.cuh"
 
@@ -52,9 +52,8 @@ int morton_sort_typed(grace_b200_ctx* ctx, float* d_spheres4, size_t n, int key_
         rc = gb_launch_morton_keys_fused<KeyT>(ctx, d_spheres4, n, d_bounds, nullptr, keys, hist, passes, (float*)tmp, st);
     }
     if (rc) return rc;
-    rc = gb_sort_pairs<KeyT>(ctx, keys, keys, perm, n, sort_bits, ws, hist, st);
-    if (rc) return rc;
-    rc = gb_gather_records(tmp, d_spheres4, perm, n, 16, ctx->sm_count, st);
+    // the last radix pass writes the spheres to their sorted places (no permutation, no separate gather launch)
+    rc = gb_sort_pairs<KeyT>(ctx, keys, d_keys_out ? keys : nullptr, perm, n, sort_bits, ws, hist, st, tmp, d_spheres4);
     if (rc) return rc;
     if (d_keys_out)
         GB_CUDA(cudaMemcpyAsync(d_keys_out, keys, n * sizeof(KeyT), cudaMemcpyDeviceToDevice, st));

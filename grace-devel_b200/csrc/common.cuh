@@ -52,6 +52,7 @@ enum {
     GB_SC_TICKET0 = 0,      // generic block tickets (self-resetting)
     GB_SC_TICKET1 = 1,
     GB_SC_NLEAVES = 2,      // leaf count of the last build
+    GB_SC_TICKET2 = 3,      // group tickets of the node build
     GB_SC_TRACE_CTR = 4,    // packet scheduler counter
     GB_SC_ERRFLAG = 5,      // device-side error flag (trace stack overflow)
     GB_SC_TOTAL64 = 8,      // 64-bit total (2 ints), 8-byte aligned

@@ -97,12 +97,16 @@ digit_scan_kernel(const uint32_t* __restrict__ hist, uint32_t* __restrict__ base
 #ifndef OS_IPT64
 #define OS_IPT64 12
 #endif
-template <typename KeyT, int NT, int IPT>
+// GATHER (last pass of the keys + sort entry point): instead of the (key, index) pair, the 16-byte record
+// the index names is written to the sorted position -- the separate gather launch read the permutation
+// back and wrote the same records; the keys are still written when the caller wants them.
+template <typename KeyT, int NT, int IPT, bool GATHER>
 __global__ void __launch_bounds__(NT, OS_MINB)
 onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                 KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                 uint32_t n, int shift, const uint32_t* __restrict__ base,
-                uint32_t* __restrict__ tile_state, uint32_t* __restrict__ tile_counter)
+                uint32_t* __restrict__ tile_state, uint32_t* __restrict__ tile_counter,
+                const float4* __restrict__ rec_in, float4* __restrict__ rec_out)
 {
     constexpr int NW = NT / 32;
     constexpr int TILE = NT * IPT;
@@ -234,12 +238,35 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ v
     }
     __syncthreads();
     // ---- write digit runs contiguously ----
-    for (uint32_t p = tid; p < n_valid; p += NT) {
-        const KeyT k = s_keys[p];
-        const unsigned d = (unsigned)(k >> shift) & (GB_RADIX - 1);
-        const uint32_t dst = digit_global[d] + p;
-        keys_out[dst] = k;
-        vals_out[dst] = s_vals[p];
+    if (GATHER) {
+#pragma unroll
+        for (int i0 = 0; i0 < IPT; i0 += 4) {
+            float4 r[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t p = (uint32_t)tid + (uint32_t)(i0 + u) * NT;
+                if (p < n_valid) r[u] = __ldg(rec_in + s_vals[p]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t p = (uint32_t)tid + (uint32_t)(i0 + u) * NT;
+                if (p < n_valid) {
+                    const KeyT k = s_keys[p];
+                    const unsigned d = (unsigned)(k >> shift) & (GB_RADIX - 1);
+                    const uint32_t dst = digit_global[d] + p;
+                    rec_out[dst] = r[u];
+                    if (keys_out) keys_out[dst] = k;
+                }
+            }
+        }
+    } else {
+        for (uint32_t p = tid; p < n_valid; p += NT) {
+            const KeyT k = s_keys[p];
+            const unsigned d = (unsigned)(k >> shift) & (GB_RADIX - 1);
+            const uint32_t dst = digit_global[d] + p;
+            keys_out[dst] = k;
+            vals_out[dst] = s_vals[p];
+        }
     }
 }
 
@@ -311,7 +338,7 @@ size_t gb_sort_workspace_bytes(size_t n, int key_bytes)
 template <typename KeyT>
 int gb_sort_pairs(grace_b200_ctx* ctx, const KeyT* d_keys_in, KeyT* d_keys_out,
                   uint32_t* d_perm_out, size_t n, int key_bits, void* ws,
-                  const uint32_t* d_hist_in, cudaStream_t st)
+                  const uint32_t* d_hist_in, cudaStream_t st, const void* d_rec16_in, void* d_rec16_out)
 {
     using C = SortCfg<KeyT>;
     constexpr int TILE = C::NT * C::IPT;
@@ -345,17 +372,26 @@ int gb_sort_pairs(grace_b200_ctx* ctx, const KeyT* d_keys_in, KeyT* d_keys_out,
     GB_LAUNCH_CHECK();
 
     constexpr size_t smem = onesweep_smem<KeyT>();
-    GB_CUDA(cudaFuncSetAttribute(onesweep_kernel<KeyT, C::NT, C::IPT>,
+    static_assert(C::IPT % 4 == 0, "the gathering write phase handles four items at a time");
+    GB_CUDA(cudaFuncSetAttribute(onesweep_kernel<KeyT, C::NT, C::IPT, false>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GB_CUDA(cudaFuncSetAttribute(onesweep_kernel<KeyT, C::NT, C::IPT, true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool fuse = d_rec16_in && d_rec16_out && passes > 1;
     const KeyT* kin = d_keys_in;
     const uint32_t* vin = nullptr;
     for (int p = 0; p < passes; ++p) {
         const bool last = (p == passes - 1);
         KeyT* kout = (last && passes > 1) ? d_keys_out : kbuf[p & 1];
         uint32_t* vout = (last && passes > 1) ? d_perm_out : vbuf[p & 1];
-        onesweep_kernel<KeyT, C::NT, C::IPT><<<(int)tiles, C::NT, smem, st>>>(
-            kin, vin, kout, vout, (uint32_t)n, p * GB_RADIX_BITS, base + p * GB_RADIX,
-            states + (size_t)p * tiles * GB_RADIX, counters + p);
+        if (last && fuse)       // records to their sorted places; keys only if asked for, the permutation not at all
+            onesweep_kernel<KeyT, C::NT, C::IPT, true><<<(int)tiles, C::NT, smem, st>>>(
+                kin, vin, d_keys_out, nullptr, (uint32_t)n, p * GB_RADIX_BITS, base + p * GB_RADIX,
+                states + (size_t)p * tiles * GB_RADIX, counters + p, (const float4*)d_rec16_in, (float4*)d_rec16_out);
+        else
+            onesweep_kernel<KeyT, C::NT, C::IPT, false><<<(int)tiles, C::NT, smem, st>>>(
+                kin, vin, kout, vout, (uint32_t)n, p * GB_RADIX_BITS, base + p * GB_RADIX,
+                states + (size_t)p * tiles * GB_RADIX, counters + p, nullptr, nullptr);
         GB_LAUNCH_CHECK();
         kin = kout;
         vin = vout;
@@ -368,9 +404,9 @@ int gb_sort_pairs(grace_b200_ctx* ctx, const KeyT* d_keys_in, KeyT* d_keys_out,
 }
 
 template int gb_sort_pairs<uint32_t>(grace_b200_ctx*, const uint32_t*, uint32_t*, uint32_t*, size_t,
-                                     int, void*, const uint32_t*, cudaStream_t);
+                                     int, void*, const uint32_t*, cudaStream_t, const void*, void*);
 template int gb_sort_pairs<uint64_t>(grace_b200_ctx*, const uint64_t*, uint64_t*, uint32_t*, size_t,
-                                     int, void*, const uint32_t*, cudaStream_t);
+                                     int, void*, const uint32_t*, cudaStream_t, const void*, void*);
 
 int gb_gather_records(const void* d_in, void* d_out, const uint32_t* d_perm, size_t n,
                       int rec_bytes, int sm_count, cudaStream_t st)
