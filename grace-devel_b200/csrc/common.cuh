@@ -37,6 +37,7 @@ struct grace_b200_ctx {
     int leaves_stage_delta_type = 0;
     int trace_mode = GRACE_B200_TRACE_PACKET;
     int trace_budget = 64;     // traversal steps before a unit may donate / be suspended (0 = never)
+    int trace_budget_set = 0;  // the caller has chosen it (else 16 for work stealing, 64 for the hit-list rounds)
     // L2 residency for the node array during traversal (the dependent node fetch is the latency chain)
     size_t l2_persist_max = 0, l2_window_max = 0;
     int l2_persist = 0;             // 1: set an access-policy window on the nodes around trace launches

@@ -366,6 +366,29 @@ __device__ __forceinline__ int pk_rec_close(PkWarp<MODE, M4>& W, int* slot_ctr, 
 template <int MODE, int M4>
 __device__ __noinline__ float pk_flush_cum(PkWarp<MODE, M4>& W, int qn, float cum, int lane, unsigned lt, const double2* table)
 {
+#ifndef PK_NO_OWN_FLUSH
+    // Well-filled FIFOs: every lane evaluates and adds its own cells -- no work list, no write-back.  The list
+    // (cells spread evenly over the lanes) only pays when few lanes hold most of the cells; instruction counts
+    // of the two paths from the SASS: ~33 per row here, ~116 + 38 per 32 listed cells there.  Same arithmetic,
+    // same order per ray.
+    if (!W.ch_on) {
+        const int rows = __reduce_max_sync(0xffffffffu, qn), total = __reduce_add_sync(0xffffffffu, qn);
+        if (rows * 33 <= 116 + ((total + 31) >> 5) * 38) {
+            __syncwarp();       // entries may have been written by other lanes (transposed leaves)
+#pragma unroll
+            for (int j = 0; j < PK_QD; ++j) {
+                if (j < rows) {
+                    if (j < qn) {
+                        const float2 e = W.q[j * 32 + lane];
+                        cum = __fmaf_rn(pk_lerp(e.x, e.y, table), __fmul_rn(e.y, e.y), cum);
+                    }
+                }
+            }
+            __syncwarp();
+            return cum;
+        }
+    }
+#endif
     pk_flush_eval<MODE, M4>(W, qn, lane, lt, table);
     if (W.ch_on) {            // recording task: the terms go to the chain, the fold launch adds them
         pk_chain_append<MODE, M4>(W, qn, lane, lt);

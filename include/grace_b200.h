@@ -210,13 +210,14 @@ int grace_b200_set_trace_mode(grace_b200_ctx* ctx, int mode);
  * ascending primitive order, so results are unaffected); a unit can be robbed once it has run
  * `steps` inner-node + leaf visits.  Hit lists: once every packet of a launch has been claimed, a
  * packet still running after `steps` visits is suspended and resumed as tasks over disjoint
- * subsets of its rays.  0 disables both; the default is 64.  OR-ing GRACE_B200_BUDGET_EAGER into
+ * subsets of its rays.  0 disables both; the default is 16 for work stealing and 64 for the hit-list rounds.  OR-ing GRACE_B200_BUDGET_EAGER into
  * `steps` makes any subtree worth stealing and suspends every hit-list unit at `steps` whether or
  * not unclaimed work is left (used by the tests to force splits). */
 #define GRACE_B200_BUDGET_EAGER (1 << 30)
 int grace_b200_set_trace_budget(grace_b200_ctx* ctx, int steps);
 /* (Also the pool in which grace_b200_trace_hits_count_f4 records the hits themselves, 16 bytes each, so that
- * grace_b200_trace_hits_fill_f4 needs no second traversal; default there: 32 KiB per ray, 256 MiB to 4 GiB.)
+ * grace_b200_trace_hits_fill_f4 needs no second traversal; default there: 32 KiB per ray, 256 MiB to 4 GiB,
+ * and a call whose pool overflowed -- it falls back to the second traversal -- sizes the next call's pool.)
  * Bytes of workspace for the per-hit terms {W, 1/h^2} that column-density tasks record for the
  * ordered final sum; 0 (default) sizes it from the ray count (64 KiB per ray, 64 MiB to 2 GiB).
  * A pool that runs dry costs time, not correctness: the affected subtrees are walked again by the
