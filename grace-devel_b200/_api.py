@@ -32,7 +32,7 @@ __all__ = [
     "uniform_random_rays", "uniform_random_rays_single_octant", "one_to_many_rays",
     "plane_parallel_random_rays", "orthographic_projection_rays", "pinhole_camera_rays",
     "healpix_rays", "synth_gadget_spheres", "exclusive_segmented_scan",
-    "weighted_exclusive_segmented_scan", "offsets_to_segments", "read_gadget", "write_gadget", "gadget_info", "context", "lib", "build_tree", "set_trace_mode", "set_trace_budget", "set_trace_pool", "trace_balance_stats", "device_error", "sharded_trace", "tiles_of_rank", "take_local", "scatter_back",
+    "weighted_exclusive_segmented_scan", "offsets_to_segments", "read_gadget", "write_gadget", "gadget_info", "context", "lib", "build_tree", "set_trace_mode", "set_trace_budget", "set_trace_pool", "set_hit_list_passes", "trace_balance_stats", "device_error", "sharded_trace", "tiles_of_rank", "take_local", "scatter_back",
 ]
 
 _c = ctypes
@@ -197,11 +197,17 @@ def set_trace_pool(nbytes):
     _check(_sig("grace_b200_set_trace_pool", [_P, _sz])(context(), int(nbytes)))
 
 
+def set_hit_list_passes(passes):
+    """1 (default): trace_sph records the hits during the counting traversal; 2: count, then fill (the reference's scheme)."""
+    _check(_sig("grace_b200_set_hit_list_passes", [_P, _c.c_int])(context(), int(passes)))
+
+
 def trace_balance_stats():
-    """Diagnostic: work-stealing counters of the last hit-count / column-density call."""
+    """Diagnostic: work-stealing counters of the last hit-count / column-density / hit-list count call
+    (overflow: the pool recording the hit lists ran dry and the fill call traversed again)."""
     out = (_c.c_int * 8)()
     _check(_sig("grace_b200_trace_balance_stats", [_P, _P, _P])(context(), out, _stream()))
-    return dict(finished=out[0], tasks=out[1], chunks=out[5], robbed=out[6])
+    return dict(finished=out[0], tasks=out[1], chunks=out[5], robbed=out[6], overflow=out[7])
 
 
 def device_error():

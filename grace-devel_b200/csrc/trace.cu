@@ -808,6 +808,14 @@ int grace_b200_set_trace_pool(grace_b200_ctx* ctx, size_t bytes)
     return GRACE_B200_OK;
 }
 
+int grace_b200_set_hit_list_passes(grace_b200_ctx* ctx, int passes)
+{
+    GB_REQUIRE(ctx && (passes == 1 || passes == 2), GRACE_B200_EINVAL, "passes must be 1 or 2");
+    ctx->one_pass_lists = passes == 1;
+    ctx->rec_valid = 0;
+    return GRACE_B200_OK;
+}
+
 int grace_b200_set_trace_mode(grace_b200_ctx* ctx, int mode)
 {
     GB_REQUIRE(ctx, GRACE_B200_EINVAL, "ctx is NULL");

@@ -223,9 +223,15 @@ int grace_b200_set_trace_budget(grace_b200_ctx* ctx, int steps);
  * A pool that runs dry costs time, not correctness: the affected subtrees are walked again by the
  * launch that adds the terms up. */
 int grace_b200_set_trace_pool(grace_b200_ctx* ctx, size_t bytes);
+/* Hit lists (grace_b200_trace_hits_count_f4 + _fill_f4, grace_b200_trace_sorted_tiles_f4): 1 (default) = ONE
+ * traversal -- the count call records the hits, the fill call copies them to the caller's arrays; 2 = two
+ * traversals (count, then fill), the reference's scheme (cuda/trace_sph.cuh:112-168), also what a call falls
+ * back to when the recording pool overflows.  Same lists either way. */
+int grace_b200_set_hit_list_passes(grace_b200_ctx* ctx, int passes);
 /* Diagnostic: counters of the last hit-count / column-density call's work stealing:
  * h_stats8 = {units finished, subtrees stolen (tasks), -, -, -, chunks of the term pool taken,
- * packets robbed, -}.  Synchronises the stream. */
+ * packets robbed (hit-list recording: slots of the copy order), hit-list recording: pool overflowed}.
+ * Synchronises the stream. */
 int grace_b200_trace_balance_stats(grace_b200_ctx* ctx, int* h_stats8, void* stream);
 /* Device-side error flag of the last trace launch: 0 = none, 1 = traversal stack overflow
  * (the reference asserts on this only under GRACE_DEBUG, bintree_trace.cuh:162-164),

@@ -27,6 +27,10 @@ json.dump({"dram_bytes_per_launch": r + w, "dram_bytes_read": r, "dram_bytes_wri
                    "with work stealing, 2^24 particles, 2^23 rays)"},
           open("profiles/trace_traffic.json", "w"), indent=1)
 PY
+[ -f gpurun_out/build_$TAG.ncu-rep ] && python scripts/ncu_summary.py gpurun_out/build_$TAG.ncu-rep > profiles/${R}_build_kernels_ncu_full.json
+[ -f gpurun_out/lists_$TAG.ncu-rep ] && python scripts/ncu_summary.py gpurun_out/lists_$TAG.ncu-rep > profiles/${R}_hit_lists_ncu_full.json
+[ -f gpurun_out/hit_lists_$TAG.jsonl ] && grep '^{' gpurun_out/hit_lists_$TAG.jsonl > profiles/${R}_hit_lists_one_vs_two_traversals.jsonl
+[ -f gpurun_out/build_times_$TAG.json ] && grep '^{' gpurun_out/build_times_$TAG.json > profiles/${R}_build_times.json
 cp gpurun_out/launches_$TAG.csv profiles/${R}_launches.csv
 cp gpurun_out/bench_$TAG.json profiles/${R}_bench_n1.json
 [ -f gpurun_out/bench_ref_$TAG.json ] && cp gpurun_out/bench_ref_$TAG.json profiles/${R}_bench_reference_arm.json

@@ -175,6 +175,28 @@ def test_tree_other_deltas(gb, orc, delta, bits):
     assert_tree_equal(out[3], out[7])
 
 
+@pytest.mark.parametrize("n", [34, 63, 64, 65, 97, 8127, 8128, 8129, 8160, 8161, 16257, 100003])
+def test_tree_default_leaf_size_edges(gb, orc, n):
+    """max_per_leaf = 32 takes the sliding-window kernel (one thread per block of 32 deltas, a CTA emits 254
+    blocks = 8128 nodes): sizes around its block and tile boundaries, and coarse coordinates so that many
+    deltas are EQUAL (the leftmost-maximum tie rule decides where leaves end)."""
+    s = clustered_spheres(n, seed=n)
+    out = build_both(gb, orc, s, 32)
+    assert_tree_equal(out[3], out[7])
+    q = s.copy()
+    q[:, :3] = np.round(q[:, :3] * 64.0) / 64.0          # a 64^3 lattice: runs of equal keys and equal distances
+    out = build_both(gb, orc, q, 32)
+    assert_tree_equal(out[3], out[7])
+
+
+@pytest.mark.parametrize("delta,bits", [("xor", 30), ("xor", 63), ("sarea", 30)])
+def test_tree_default_leaf_size_other_deltas(gb, orc, delta, bits):
+    s = clustered_spheres(70001, seed=5)
+    s[:, :3] = np.round(s[:, :3] * 256.0) / 256.0
+    out = build_both(gb, orc, s, 32, bits=bits, delta=delta)
+    assert_tree_equal(out[3], out[7])
+
+
 def test_tree_tiny_and_errors(gb, orc):
     s = np.array([[-0.5, -0.5, -0.5, 0.2], [0.5, 0.5, 0.5, 0.2]], np.float32)
     out = build_both(gb, orc, s, 1, bot=-np.ones(3, np.float32), top=np.ones(3, np.float32))
@@ -299,6 +321,58 @@ def test_packet_splitting_is_exact(gb, orc, scene, budget, pool, trace_mode):
     finally:
         gb.set_trace_budget(1024)
         gb.set_trace_pool(0)
+
+
+def test_hit_lists_one_traversal_equals_two(gb, orc, scene, trace_mode):
+    """trace_sph records the hits during the counting traversal (work stealing, nested thefts) and copies them;
+    the lists must equal those of count-then-fill, entry for entry, also when the recording pool overflows
+    (fallback to the second traversal) -- after which the context asks for a pool that fits."""
+    if trace_mode != "packet":
+        pytest.skip("recording exists only in the production packet schedule")
+    d_s, tree, hs, htree, rays = scene
+    sub = dev(rays)
+    nr = len(rays)
+    off2 = torch.empty(nr, dtype=torch.int32, device="cuda")
+    gb.set_hit_list_passes(2)
+    try:
+        want = gb.trace_sph(sub, d_s, tree, off2)
+    finally:
+        gb.set_hit_list_passes(1)
+    for budget, eager in ((8, True), (16, False)):
+        gb.set_trace_budget(budget, eager=eager)
+        try:
+            off = torch.empty(nr, dtype=torch.int32, device="cuda")
+            got = gb.trace_sph(sub, d_s, tree, off)
+            st = gb.trace_balance_stats()
+            assert st["overflow"] == 0, "the default pool must hold the hits of these rays"
+            if eager:
+                assert st["tasks"] > 0, "an eager budget of 8 steps must lead to thefts"
+            assert torch.equal(off, off2)
+            for a, b in zip(got, want):
+                assert torch.equal(a.view(torch.int32), b.view(torch.int32))
+        finally:
+            gb.set_trace_budget(1024)
+    # a pool of 64 chunks overflows: same lists through the fallback, and the next call's pool is sized from this one
+    gb.set_trace_pool(64 * 8192)
+    try:
+        for expect_overflow in (1, 0):
+            off = torch.empty(nr, dtype=torch.int32, device="cuda")
+            got = gb.trace_sph(sub, d_s, tree, off)
+            assert gb.trace_balance_stats()["overflow"] == expect_overflow
+            assert torch.equal(off, off2)
+            for a, b in zip(got, want):
+                assert torch.equal(a.view(torch.int32), b.view(torch.int32))
+    finally:
+        gb.set_trace_pool(0)
+    # with sentinels: every ray's segment ends with one slot holding them
+    idx, integ, dist = gb.trace_with_sentinels_sph(sub, d_s, tree, off, -7, -1.0, 1e30)
+    o = off.cpu().numpy().astype(np.int64); o2 = off2.cpu().numpy().astype(np.int64)
+    assert np.array_equal(o, o2 + np.arange(nr))
+    ends = np.concatenate([o[1:], [idx.numel()]]) - 1
+    assert np.all(idx.cpu().numpy()[ends] == -7) and np.all(dist.cpu().numpy()[ends] == np.float32(1e30))
+    keep = np.ones(idx.numel(), bool); keep[ends] = False
+    assert np.array_equal(idx.cpu().numpy()[keep], want[0].cpu().numpy())
+    assert np.array_equal(dist.cpu().numpy()[keep].view(np.uint32), want[2].cpu().numpy().view(np.uint32))
 
 
 def test_default_splitting_small_launches(gb, orc, scene):
