@@ -1449,6 +1449,10 @@ __global__ void __launch_bounds__(256) rec_copy_kernel(const char* __restrict__ 
     const int n_chunks = min(__ldg(pool_ctr), pool_cap);
     const int n_warps = gridDim.x * (blockDim.x >> 5);
     const int n_groups = (n_chunks + PK_COPY_G - 1) / PK_COPY_G;
+    // the caller's arrays are written in runs of a few hits per ray: keep their lines in L2 until the neighbouring
+    // runs have arrived (and for the sort that usually follows)
+    unsigned long long pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
     for (int grp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); grp < n_groups; grp += n_warps) {
         int my_chunk = -1;
         if (lane < PK_COPY_G && grp * PK_COPY_G + lane < n_chunks) my_chunk = __ldg(order + grp * PK_COPY_G + lane);
@@ -1478,7 +1482,9 @@ __global__ void __launch_bounds__(256) rec_copy_kernel(const char* __restrict__ 
                     const int b = __shfl_sync(0xffffffffu, base, code & 31);
                     if (k < n) {
                         const int pos = b + (int)((unsigned)code >> 5);
-                        hit_integral[pos] = v[u].x; hit_dist[pos] = v[u].y; hit_idx[pos] = __float_as_int(v[u].z);
+                        asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" :: "l"(hit_integral + pos), "f"(v[u].x), "l"(pol) : "memory");
+                        asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" :: "l"(hit_dist + pos), "f"(v[u].y), "l"(pol) : "memory");
+                        asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" :: "l"(hit_idx + pos), "f"(v[u].z), "l"(pol) : "memory");
                     }
                 }
             }
