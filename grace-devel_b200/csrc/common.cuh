@@ -56,6 +56,7 @@ enum {
     GB_SC_TICKET2 = 3,      // group tickets of the node build
     GB_SC_TRACE_CTR = 4,    // packet scheduler counter
     GB_SC_ERRFLAG = 5,      // device-side error flag (trace stack overflow)
+    GB_SC_TICKET3 = 6,      // segment tickets of the segmented scans (zeroed before every launch; TICKET0 must be 0 between launches)
     GB_SC_TOTAL64 = 8,      // 64-bit total (2 ints), 8-byte aligned
     GB_SC_TASKS = 32,       // trace load balancing: record count + two task-list counts
     GB_SC_CLASS = 40,       // segmented sort class counters (16 ints) + XL total (2 ints, 8-byte aligned)

@@ -93,7 +93,8 @@ int launch_segscan(grace_b200_ctx* ctx, const int* d_offsets, size_t n_segments,
     GB_REQUIRE(n_segments < (1ull << 31) && n_data < (1ull << 31), GRACE_B200_ERANGE,
                "segment offsets are 32-bit (cuda/scan.cuh:16)");
     if (n_segments == 0 || n_data == 0) return GRACE_B200_OK;
-    unsigned* ticket = (unsigned*)(ctx->d_scalars + GB_SC_TICKET0);
+    // its own counter: the bounds kernel's ticket (TICKET0) resets itself and must be zero between launches
+    unsigned* ticket = (unsigned*)(ctx->d_scalars + GB_SC_TICKET3);
     GB_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
     size_t blocks = (n_segments + SS_THREADS / 32 - 1) / (SS_THREADS / 32);
     const size_t cap = (size_t)ctx->sm_count * 8;

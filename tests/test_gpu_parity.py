@@ -564,6 +564,11 @@ def test_segmented_scans(gb, count, max_seg, empty):
         flags[1] = 1
         flags[2:] = off[2:] != off[1:-1]
     assert np.array_equal(host(segs), np.cumsum(flags)[seg_id])
+    # calls sharing the context's device scalars must not disturb each other: bounds right after a segmented scan
+    # (the scan's ticket counter used to be the bounds kernel's, which expects to find it zero)
+    pts = uniform_spheres(70000, seed=9)
+    lo, hi = gb.min_max_x(dev(pts))
+    assert lo == float(pts[:, 0].min()) and hi == float(pts[:, 0].max())
 
 
 @pytest.mark.parametrize("nside", [1, 4, 64, 1024])
