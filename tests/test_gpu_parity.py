@@ -375,6 +375,32 @@ def test_hit_lists_one_traversal_equals_two(gb, orc, scene, trace_mode):
     assert np.array_equal(dist.cpu().numpy()[keep].view(np.uint32), want[2].cpu().numpy().view(np.uint32))
 
 
+@pytest.mark.parametrize("mpl", [1, 8, 64, 100])
+def test_hit_lists_other_leaf_sizes(gb, orc, mpl, trace_mode):
+    """Hit lists recorded during the counting traversal for leaves of 1 ... 100 primitives (the 32-, 64- and
+    128-sphere staging variants of the packet kernel), thefts forced: equal to the oracle entry for entry, and
+    to the two-traversal scheme."""
+    if trace_mode != "packet":
+        pytest.skip("recording exists only in the production packet schedule")
+    s = clustered_spheres(40000, seed=100 + mpl)
+    d_s, _, _, tree, hs, _, _, htree = build_both(gb, orc, s, mpl)
+    rays = isotropic_rays(1024, origin=(0.5, 0.5, 0.5), length=2.0, seed=mpl)
+    roff, ridx, rinteg, rdist = orc.trace_hits(rays, hs, htree)
+    gb.set_trace_budget(8, eager=True)
+    try:
+        for passes in (1, 2):
+            gb.set_hit_list_passes(passes)
+            off = torch.empty(len(rays), dtype=torch.int32, device="cuda")
+            idx, integ, dist = gb.trace_sph(dev(rays), d_s, tree, off)
+            assert gb.device_error() == 0
+            assert np.array_equal(host(off), roff) and np.array_equal(host(idx), ridx)
+            assert np.array_equal(host(integ).view(np.uint32), rinteg.view(np.uint32))
+            assert np.array_equal(host(dist).view(np.uint32), rdist.view(np.uint32))
+    finally:
+        gb.set_hit_list_passes(1)
+        gb.set_trace_budget(1024)
+
+
 def test_default_splitting_small_launches(gb, orc, scene):
     """The default policy on launches far smaller than the grid (every packet is suspended at the
     budget and its subtrees spread over the idle warps): results still exact."""
