@@ -441,6 +441,7 @@ trace_ray_kernel(const grace_b200_ray* __restrict__ rays, int n_packets,
 }
 
 #include "trace_packet.cuh"
+#include "rec_lists.cuh"
 
 size_t trace_smem_bytes(int max_per_leaf)
 {
@@ -545,7 +546,7 @@ int launch_packet(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, int n_packe
             pool_bytes = gb_align((size_t)pool_cap * PK_CH_BYTES);
         }
         const size_t adv_bytes = gb_align(PK_ADV * sizeof(int));
-        const size_t order_bytes = RECM ? gb_align((size_t)pool_cap * sizeof(int)) : 0;       // hit records: the copy order
+        const size_t order_bytes = RECM ? gb_align((size_t)pool_cap * PK_COPY_G * sizeof(int)) : 0;       // hit records: the copy order (groups of chunks)
         char* w = (char*)gb_workspace(ctx, GB_WS_HEAD + rec_bytes + 2 * slot_bytes + adv_bytes + roots_bytes + rcum_bytes + order_bytes + pool_bytes);
         if (!w) return GRACE_B200_ENOMEM;
         int* lb = ctx->d_scalars + GB_SC_LB;
@@ -574,6 +575,7 @@ int launch_packet(grace_b200_ctx* ctx, const grace_b200_ray* d_rays, int n_packe
         GB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
         // robbed packets and their tasks add into the same cells
         if (KMODE == MODE_COUNT || RECM) GB_CUDA(cudaMemsetAsync(out_counts, 0, (size_t)n_packets * 32 * sizeof(int), st));
+        if (RECM) GB_CUDA(cudaMemsetAsync(T.order, 0xff, order_bytes, st));      // -1: no chunk
         // the whole grid: the warps that get no packet are the first thieves
         kernel<<<full_grid, PK_THREADS, psmem, st>>>(P, T);
         GB_LAUNCH_CHECK();
@@ -750,7 +752,14 @@ int gb_trace_copy_recorded(grace_b200_ctx* ctx, const int* d_offsets, int* d_idx
     PkArgs P; PkTasks T;
     memcpy(&P, ctx->rec_blob, sizeof(PkArgs));
     memcpy(&T, ctx->rec_blob + sizeof(PkArgs), sizeof(PkTasks));
-    rec_copy_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(T.pool, T.pool_ctr, T.pool_cap, T.order, T.records, d_offsets, d_idx, d_integ, d_dist);
+    static bool attr_set = false;
+    if (!attr_set) {
+        GB_CUDA(cudaFuncSetAttribute(rec_copy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RC_WARPS * sizeof(RcWarp))));
+        attr_set = true;
+    }
+    // groups <= chunks; the group count is in the slot counter the units drew from
+    rec_copy_kernel<<<ctx->sm_count * 3, RC_WARPS * 32, RC_WARPS * sizeof(RcWarp), st>>>(T.pool, T.n_roots, T.pool_cap, T.order, T.records, d_offsets,
+                                                                                        d_idx, d_integ, d_dist);
     GB_LAUNCH_CHECK();
     return GRACE_B200_OK;
 }
@@ -805,6 +814,7 @@ int grace_b200_set_trace_pool(grace_b200_ctx* ctx, size_t bytes)
 {
     GB_REQUIRE(ctx, GRACE_B200_EINVAL, "ctx is NULL");
     ctx->trace_pool_bytes = bytes;
+    ctx->rec_pool_learned = 0;        // what earlier hit-list recordings would have needed is forgotten
     return GRACE_B200_OK;
 }
 

@@ -283,11 +283,12 @@ __device__ __noinline__ float pk_fold_chain(const char* pool, int head, float cu
 //     {integral, distance, primitive index, (k << 5) | lane}
 // where k says that this is the k-th hit of ray `lane` WITHIN THE UNIT (a packet, or a stolen subtree of
 // one).  Entries are self-describing, so a chunk can be copied to the caller's arrays by any warp once
-// the position of its unit's first hit is known for each ray (rec_resolve_kernel below); no chain has to
+// the position of its unit's first hit is known for each ray (rec_resolve_kernel, rec_lists.cuh); no chain has to
 // be walked.  A flush lists the occupied FIFO cells ray-major exactly like pk_flush_fill, so the copy's
 // stores land on a few contiguous stretches; it may straddle two chunks, nothing is padded.
 constexpr int PK_RCH_BYTES = 8192;
 constexpr int PK_RCH_CAP = (PK_RCH_BYTES - 32) / 16;
+constexpr int PK_COPY_G = 4;                  // chunks of one unit that are copied together (rec_lists.cuh)
 constexpr int PK_RCH_MAXK = 1 << 26;          // hits of one ray within one unit that (k << 5 | lane) can hold
 
 template <int MODE, int M4>
@@ -346,9 +347,8 @@ __device__ __noinline__ int pk_flush_rec(PkWarp<MODE, M4>& W, int qn, int count,
 }
 
 // The unit is finished: header of its last chunk.  Returns the first of the consecutive slots of the copy
-// order that the unit's chunks take (its k-th chunk is copied k-th of them, by the same or a neighbouring
-// warp at about the same time: a ray's hits of consecutive chunks are neighbours in the caller's arrays, and
-// the sectors they share are completed while still in L2).
+// order that the unit takes, one per group of PK_COPY_G consecutive chunks (a group is copied by one warp:
+// for every ray it holds a run of consecutive hits of that ray).
 template <int MODE, int M4>
 __device__ __forceinline__ int pk_rec_close(PkWarp<MODE, M4>& W, int* slot_ctr, int lane)
 {
@@ -358,7 +358,7 @@ __device__ __forceinline__ int pk_rec_close(PkWarp<MODE, M4>& W, int* slot_ctr, 
     if (cur >= 0 && lane == 0) {
         const int nb = W.ch_nb;
         *(int4*)(W.pool + (size_t)cur * PK_RCH_BYTES) = make_int4(W.ch_off, W.ch_unit, nb - 1, 0);
-        start = atomicAdd(slot_ctr, nb);
+        start = atomicAdd(slot_ctr, (nb + PK_COPY_G - 1) / PK_COPY_G);
     }
     return start;      // lane 0's is the one
 }
@@ -1375,119 +1375,6 @@ trace_packet_kernel(const __grid_constant__ PkArgs P, const __grid_constant__ Pk
 #ifdef PK_PROF_LANES
             pp[1] = pf_l1; pp[2] = pf_l2; pp[3] = pf_l3;
 #endif
-        }
-    }
-}
-
-// ---- one-pass hit lists: where each unit's hits start, then the copy ----
-// Traversal order of a ray's hits: the unit's own, then what was stolen from it, latest theft first
-// (thefts take the BOTTOM of the stack, i.e. what the unit would have walked last), each stolen subtree
-// recursively the same.  So a pre-order walk of a packet's theft tree with a running per-ray position
-// gives every task the position of its first hit; it is stored in the second half of the task's record
-// (the first half holds its own hit count per ray).  One warp per robbed packet, lane = ray.
-constexpr int PK_RESOLVE_DEPTH = 128;
-__global__ void __launch_bounds__(128) rec_resolve_kernel(const int2* __restrict__ roots, const int* __restrict__ root_own,
-                                                         int* records, const int* __restrict__ offsets, int n_packets,
-                                                         const int* __restrict__ created_ptr, int records_cap, int* overflow)
-{
-    const int created = min(__ldg(created_ptr), records_cap);
-    __shared__ int stk[4][PK_RESOLVE_DEPTH];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int packet = blockIdx.x * 4 + w; packet < n_packets; packet += gridDim.x * 4) {
-        int node = __ldg(&roots[packet].y);
-        if (node < 0) continue;
-        int cur = __ldg(offsets + packet * 32 + lane) + __ldg(root_own + packet * 32 + lane);
-        int sp = 0;
-        for (int guard = 0;; ++guard) {
-            if (node < 0) {
-                if (sp == 0) break;
-                node = stk[w][--sp];
-            }
-            if (node >= created || guard > created) { if (lane == 0) atomicExch(overflow, 1); break; }     // malformed: two passes
-            int* rec = records + (size_t)node * PK_DREC_WORDS;
-            const int older = __ldcg(rec + PK_DR_OLDER), dons = __ldcg(rec + PK_DR_DONS), status = __ldcg(rec + PK_DR_STATUS);
-            const int own = __ldcg(rec + PK_DR_ENTRIES + lane);
-            if (status != 1) { if (lane == 0) atomicExch(overflow, 1); break; }
-            rec[PK_DR_ENTRIES + 32 + lane] = cur;
-            cur += own;
-            if (older >= 0) {
-                if (sp >= PK_RESOLVE_DEPTH) { if (lane == 0) atomicExch(overflow, 1); break; }
-                __syncwarp();
-                if (lane == 0) stk[w][sp] = older;
-                ++sp;
-                __syncwarp();
-            }
-            node = dons;
-        }
-        __syncwarp();
-    }
-}
-
-// Copy order: chunk -> its slot (first slot of its unit + which of the unit's chunks it is).
-__global__ void __launch_bounds__(256) rec_order_kernel(const char* __restrict__ pool, const int* __restrict__ pool_ctr, int pool_cap,
-                                                       const int2* __restrict__ roots, const int* __restrict__ records,
-                                                       int* __restrict__ order)
-{
-    const int n_chunks = min(__ldg(pool_ctr), pool_cap);
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_chunks; c += gridDim.x * blockDim.x) {
-        const int4 h = __ldg((const int4*)(pool + (size_t)c * PK_RCH_BYTES));     // entries, unit, which, -
-        const int start = h.y >= 0 ? __ldg(&roots[h.y].x) : __ldg(records + (size_t)(-1 - h.y) * PK_DREC_WORDS + PK_DR_HEAD);
-        const int slot = start + h.z;
-        if (slot >= 0 && slot < n_chunks) order[slot] = c;
-    }
-}
-
-// Entry {integral, distance, index, k << 5 | lane} goes to position (first hit of the chunk's unit for ray
-// `lane`) + k of the caller's arrays.  A warp copies PK_COPY_G chunks that are neighbours in the copy order.
-constexpr int PK_COPY_G = 4;
-__global__ void __launch_bounds__(256) rec_copy_kernel(const char* __restrict__ pool, const int* __restrict__ pool_ctr, int pool_cap,
-                                                      const int* __restrict__ order, const int* __restrict__ records,
-                                                      const int* __restrict__ offsets,
-                                                      int* __restrict__ hit_idx, float* __restrict__ hit_integral, float* __restrict__ hit_dist)
-{
-    const int lane = threadIdx.x & 31;
-    const int n_chunks = min(__ldg(pool_ctr), pool_cap);
-    const int n_warps = gridDim.x * (blockDim.x >> 5);
-    const int n_groups = (n_chunks + PK_COPY_G - 1) / PK_COPY_G;
-    // the caller's arrays are written in runs of a few hits per ray: keep their lines in L2 until the neighbouring
-    // runs have arrived (and for the sort that usually follows)
-    unsigned long long pol;
-    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    for (int grp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); grp < n_groups; grp += n_warps) {
-        int my_chunk = -1;
-        if (lane < PK_COPY_G && grp * PK_COPY_G + lane < n_chunks) my_chunk = __ldg(order + grp * PK_COPY_G + lane);
-        int2 my_h = make_int2(0, 0);
-        if (my_chunk >= 0) my_h = __ldg((const int2*)(pool + (size_t)my_chunk * PK_RCH_BYTES));
-#pragma unroll 1
-        for (int g = 0; g < PK_COPY_G; ++g) {
-            const int chunk = __shfl_sync(0xffffffffu, my_chunk, g);
-            if (chunk < 0) break;
-            const int2 h = make_int2(__shfl_sync(0xffffffffu, my_h.x, g), __shfl_sync(0xffffffffu, my_h.y, g));         // entries, unit
-            const char* ch = pool + (size_t)chunk * PK_RCH_BYTES;
-            const int base = h.y >= 0 ? __ldg(offsets + (size_t)h.y * 32 + lane)
-                                      : __ldg(records + (size_t)(-1 - h.y) * PK_DREC_WORDS + PK_DR_ENTRIES + 32 + lane);
-            const float4* e = (const float4*)(ch + 32);
-            const int n = min(h.x, PK_RCH_CAP);
-            for (int k0 = 0; k0 < n; k0 += 256) {
-                float4 v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int k = k0 + u * 32 + lane;
-                    v[u] = k < n ? __ldcs(e + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int k = k0 + u * 32 + lane;
-                    const int code = __float_as_int(v[u].w);
-                    const int b = __shfl_sync(0xffffffffu, base, code & 31);
-                    if (k < n) {
-                        const int pos = b + (int)((unsigned)code >> 5);
-                        asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" :: "l"(hit_integral + pos), "f"(v[u].x), "l"(pol) : "memory");
-                        asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" :: "l"(hit_dist + pos), "f"(v[u].y), "l"(pol) : "memory");
-                        asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" :: "l"(hit_idx + pos), "f"(v[u].z), "l"(pol) : "memory");
-                    }
-                }
-            }
         }
     }
 }

@@ -217,7 +217,8 @@ int grace_b200_set_trace_mode(grace_b200_ctx* ctx, int mode);
 int grace_b200_set_trace_budget(grace_b200_ctx* ctx, int steps);
 /* (Also the pool in which grace_b200_trace_hits_count_f4 records the hits themselves, 16 bytes each, so that
  * grace_b200_trace_hits_fill_f4 needs no second traversal; default there: 32 KiB per ray, 256 MiB to 4 GiB,
- * and a call whose pool overflowed -- it falls back to the second traversal -- sizes the next call's pool.)
+ * and a call whose pool overflowed -- it falls back to the second traversal -- sizes the next call's pool
+ * (forgotten again when this function is called).)
  * Bytes of workspace for the per-hit terms {W, 1/h^2} that column-density tasks record for the
  * ordered final sum; 0 (default) sizes it from the ray count (64 KiB per ray, 64 MiB to 2 GiB).
  * A pool that runs dry costs time, not correctness: the affected subtrees are walked again by the
