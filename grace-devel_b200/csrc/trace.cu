@@ -752,11 +752,8 @@ int gb_trace_copy_recorded(grace_b200_ctx* ctx, const int* d_offsets, int* d_idx
     PkArgs P; PkTasks T;
     memcpy(&P, ctx->rec_blob, sizeof(PkArgs));
     memcpy(&T, ctx->rec_blob + sizeof(PkArgs), sizeof(PkTasks));
-    static bool attr_set = false;
-    if (!attr_set) {
-        GB_CUDA(cudaFuncSetAttribute(rec_copy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RC_WARPS * sizeof(RcWarp))));
-        attr_set = true;
-    }
+    // (per device, so on every call like the other launches: a process may drive several devices)
+    GB_CUDA(cudaFuncSetAttribute(rec_copy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RC_WARPS * sizeof(RcWarp))));
     // groups <= chunks; the group count is in the slot counter the units drew from
     rec_copy_kernel<<<ctx->sm_count * 3, RC_WARPS * 32, RC_WARPS * sizeof(RcWarp), st>>>(T.pool, T.n_roots, T.pool_cap, T.order, T.records, d_offsets,
                                                                                         d_idx, d_integ, d_dist);

@@ -165,7 +165,7 @@ __device__ __forceinline__ void pk_flush_eval(PkWarp<MODE, M4>& W, int qn, int l
         const float w = pk_lerp(e.x, e.y, table);
         const float ir2 = __fmul_rn(e.y, e.y);
         // per-hit value as stored (OnHit_sphere_individual): one FMUL
-        W.q[c] = (MODE == MODE_FILL || MODE == MODE_REC) ? make_float2(__fmul_rn(w, ir2), 0.f) : make_float2(w, ir2);
+        W.q[c] = MODE == MODE_FILL ? make_float2(__fmul_rn(w, ir2), 0.f) : make_float2(w, ir2);
     }
     __syncwarp();
 }
@@ -967,7 +967,7 @@ trace_packet_kernel(const __grid_constant__ PkArgs P, const __grid_constant__ Pk
     using Warp = PkWarp<MODE, M4>;
     constexpr bool NEED_Q = Warp::NEED_Q;
     constexpr bool SUB = MODE != MODE_FILL;           // subtree donation; hit lists: ray-subset rounds
-    constexpr bool CHAIN = MODE == MODE_CUMULATIVE || MODE == MODE_REC;   // ordered chains + fold / copy launch
+    constexpr bool CHAIN = MODE == MODE_CUMULATIVE || MODE == MODE_REC;   // units write to a pool: term chains + fold launch, or hit records
     constexpr bool REC = MODE == MODE_REC;            // hit lists in one traversal: EVERY unit records its hits
     extern __shared__ __align__(16) unsigned char pk_smem[];
     double2* s_table = (double2*)pk_smem;     // {T[i], T[i+1] - T[i]}
