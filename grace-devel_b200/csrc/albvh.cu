@@ -498,8 +498,72 @@ __device__ __forceinline__ void nd_merge_rounds(NdSub<T>& S, bool& active, int l
     }
 }
 
-// FROM_AABB: `spheres` holds two float4 per primitive, {bx,by,bz,-} {tx,ty,tz,-}: boxes a user's
-// AABB functor produced (generic primitives), instead of {x,y,z,h} spheres.
+// Leaf boxes, as their own pass: one lane per leaf reading its spheres straight from global memory touches 32
+// cache lines per load instruction (the L1 tag stage alone was ~100 us of the node build), so a warp stages the
+// contiguous sphere range of its 32 leaves in shared memory with coalesced cp.async, LB_SLAB spheres at a time,
+// and every lane folds the part of its own leaf that lies in the slab.  Boxes go to a scratch array
+// ({bx,by,bz,tx} {ty,tz,-,-} per leaf); the node build reads one lane's box with two coalesced loads.
+// FROM_AABB: `prims` holds two float4 per primitive, {bx,by,bz,-} {tx,ty,tz,-}: boxes a user's AABB functor
+// produced (generic primitives), instead of {x,y,z,h} spheres.
+constexpr int LB_THREADS = 256;
+constexpr int LB_SLAB = 512;
+
+template <bool FROM_AABB>
+__global__ void __launch_bounds__(LB_THREADS)
+leaf_boxes_kernel(const float4* __restrict__ prims, const int4* __restrict__ leaves, const int* __restrict__ n_leaves_ptr,
+                  float4* __restrict__ boxes)
+{
+    extern __shared__ __align__(16) unsigned char lb_smem[];
+    constexpr int PER = FROM_AABB ? 2 : 1;           // float4 per primitive
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4* slab = (float4*)lb_smem + (size_t)warp * LB_SLAB * PER;
+    const int L = *n_leaves_ptr;
+    const int rows = (L + 31) / 32;
+    const int n_warps = gridDim.x * (LB_THREADS / 32);
+    for (int row = blockIdx.x * (LB_THREADS / 32) + warp; row < rows; row += n_warps) {
+        const int leaf = row * 32 + lane;
+        const bool active = leaf < L;
+        int2 lf = make_int2(0, 0);
+        if (active) lf = __ldg((const int2*)(leaves + leaf));
+        // the row's leaves tile one contiguous range of primitives
+        const int s0 = __shfl_sync(0xffffffffu, lf.x, 0);
+        const int s1 = __shfl_sync(0xffffffffu, lf.x + lf.y, min(31, L - 1 - row * 32));
+        float bx = CUDART_INF_F, by = CUDART_INF_F, bz = CUDART_INF_F;
+        float tx = -CUDART_INF_F, ty = -CUDART_INF_F, tz = -CUDART_INF_F;
+        for (int p0 = s0; p0 < s1; p0 += LB_SLAB) {
+            const int n = min(LB_SLAB, s1 - p0);
+            __syncwarp();              // the previous slab has been read
+            const float4* src = prims + (size_t)p0 * PER;
+            for (int i = lane; i < n * PER; i += 32) {
+                const unsigned d = (unsigned)__cvta_generic_to_shared(slab + i);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(src + i) : "memory");
+            }
+            asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            const int lo = max(lf.x, p0) - p0, hi = min(lf.x + lf.y, p0 + n) - p0;
+#pragma unroll 4
+            for (int i = lo; i < hi; ++i) {
+                if (FROM_AABB) {
+                    const float4 b = slab[2 * i], t = slab[2 * i + 1];
+                    bx = fminf(bx, b.x); by = fminf(by, b.y); bz = fminf(bz, b.z);
+                    tx = fmaxf(tx, t.x); ty = fmaxf(ty, t.y); tz = fmaxf(tz, t.z);
+                } else {
+                    const float4 sp = slab[i];
+                    // AABBSphere, generic/functors/aabb.h:9-26: centre -/+ h, one FADD each
+                    bx = fminf(bx, __fsub_rn(sp.x, sp.w)); tx = fmaxf(tx, __fadd_rn(sp.x, sp.w));
+                    by = fminf(by, __fsub_rn(sp.y, sp.w)); ty = fmaxf(ty, __fadd_rn(sp.y, sp.w));
+                    bz = fminf(bz, __fsub_rn(sp.z, sp.w)); tz = fmaxf(tz, __fadd_rn(sp.z, sp.w));
+                }
+            }
+        }
+        if (active) {
+            boxes[2 * (size_t)leaf] = make_float4(bx, by, bz, tx);
+            boxes[2 * (size_t)leaf + 1] = make_float4(ty, tz, 0.f, 0.f);
+        }
+    }
+}
+
+// Node build from the leaf boxes (leaf_boxes_kernel).
 //
 // Warps are independent (no block barrier: with the block-wide stage the kernel spent its time waiting
 // for the one warp that merged the block's leftovers and for the lanes climbing with atomics): a warp
@@ -508,10 +572,9 @@ __device__ __forceinline__ void nd_merge_rounds(NdSub<T>& S, bool& active, int l
 constexpr int ND_ROWS = 4;
 constexpr int ND_GROUP = 32 * ND_ROWS;
 
-template <typename T, bool FROM_AABB>
+template <typename T>
 __global__ void __launch_bounds__(ND_THREADS)
-nodes_kernel(const float4* __restrict__ spheres, const int4* __restrict__ leaves,
-             const int* __restrict__ n_leaves_ptr, const T* __restrict__ ld_shifted,
+nodes_kernel(const float4* __restrict__ boxes, const int* __restrict__ n_leaves_ptr, const T* __restrict__ ld_shifted,
              int4* nodes, unsigned* flags, int* __restrict__ root, int* __restrict__ ticket)
 {
     extern __shared__ __align__(16) unsigned char nd_smem[];
@@ -527,43 +590,24 @@ nodes_kernel(const float4* __restrict__ spheres, const int4* __restrict__ leaves
     grp = __shfl_sync(0xffffffffu, grp, 0);
     if (grp >= n_groups) break;
     const int G = grp * ND_GROUP;
-    // the leaf records of all rows are requested first
-    int2 lfs[ND_ROWS];
+    // the leaf boxes of all rows are requested first
+    float4 bxs[ND_ROWS][2];
 #pragma unroll
     for (int row = 0; row < ND_ROWS; ++row) {
         const int leaf = G + row * 32 + lane;
-        lfs[row] = leaf < L ? __ldg((const int2*)(leaves + leaf)) : make_int2(0, 0);
+        bxs[row][0] = bxs[row][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (leaf < L) { bxs[row][0] = __ldg(boxes + 2 * (size_t)leaf); bxs[row][1] = __ldg(boxes + 2 * (size_t)leaf + 1); }
     }
     int count = 0;
-#pragma unroll 1
+#pragma unroll
     for (int row = 0; row < ND_ROWS; ++row) {
         const int leaf = G + row * 32 + lane;
         bool active = leaf < L;
         if (!__any_sync(0xffffffffu, active)) break;
         // ---- (1) leaf boxes ----
-        int2 lf = lfs[0];
-#pragma unroll
-        for (int k = 1; k < ND_ROWS; ++k) if (row == k) lf = lfs[k];
         NdSub<T> S;
-        S.bx = S.by = S.bz = CUDART_INF_F;
-        S.tx = S.ty = S.tz = -CUDART_INF_F;
-        // every lane folds its own leaf: the loads of one lane are independent (deep unrolling keeps
-        // several 16-byte loads in flight) and the warp's leaves are contiguous in memory, so all
-        // the lines it touches are consumed in full
-#pragma unroll 8
-        for (int i = 0; i < lf.y; ++i) {
-            if (FROM_AABB) {
-                const float4 b = __ldg(spheres + 2 * (size_t)(lf.x + i)), t = __ldg(spheres + 2 * (size_t)(lf.x + i) + 1);
-                S.bx = fminf(S.bx, b.x); S.by = fminf(S.by, b.y); S.bz = fminf(S.bz, b.z);
-                S.tx = fmaxf(S.tx, t.x); S.ty = fmaxf(S.ty, t.y); S.tz = fmaxf(S.tz, t.z);
-            } else {
-                const float4 s = __ldg(spheres + lf.x + i);
-                // AABBSphere, generic/functors/aabb.h:9-26: centre -/+ h, one FADD each
-                S.bx = fminf(S.bx, __fsub_rn(s.x, s.w)); S.tx = fmaxf(S.tx, __fadd_rn(s.x, s.w));
-                S.by = fminf(S.by, __fsub_rn(s.y, s.w)); S.ty = fmaxf(S.ty, __fadd_rn(s.y, s.w));
-                S.bz = fminf(S.bz, __fsub_rn(s.z, s.w)); S.tz = fmaxf(S.tz, __fadd_rn(s.z, s.w));
-            }
-        }
+        S.bx = bxs[row][0].x; S.by = bxs[row][0].y; S.bz = bxs[row][0].z;
+        S.tx = bxs[row][0].w; S.ty = bxs[row][1].x; S.tz = bxs[row][1].y;
         // ---- (2a) the row's 32 leaves ----
         S.l = S.r = leaf;
         S.cur = leaf + n_nodes;            // child index >= n_nodes marks a leaf
@@ -654,20 +698,23 @@ int grid_cap(const grace_b200_ctx* ctx, size_t work_items, int per_block, int pe
 
 // Workspace of one build: leaf-level deltas, per-node arrival flags, look-back states.
 template <typename T>
-struct BuildWs { T* leaf_deltas; unsigned* flags; unsigned long long* block_state; };
+struct BuildWs { T* leaf_deltas; unsigned* flags; unsigned long long* block_state; float4* leaf_boxes; };
 
 template <typename T>
 int build_workspace(grace_b200_ctx* ctx, size_t n, BuildWs<T>* out)
 {
     const int lv_blocks = ((int)n - 1 + LV_TILE - 1) / LV_TILE;
+    // (leaf boxes: 32 bytes per leaf, and the leaf count is only known on the device -- anything up to n; the arena of the
+    // keys + sort call that normally precedes is larger)
     const size_t bytes = gb_align((n + 1) * sizeof(T)) + gb_align(n * sizeof(unsigned)) +
-                         gb_align((size_t)lv_blocks * 8) + 256;
+                         gb_align((size_t)lv_blocks * 8) + gb_align(2 * n * sizeof(float4)) + 256;
     void* ws = gb_workspace(ctx, bytes);
     if (!ws) return GRACE_B200_ENOMEM;
     GbArena a(ws, bytes);
     out->leaf_deltas = a.take<T>(n + 1);
     out->flags = a.take<unsigned>(n);
     out->block_state = a.take<unsigned long long>(lv_blocks);
+    out->leaf_boxes = a.take<float4>(2 * n);
     return GRACE_B200_OK;
 }
 
@@ -714,26 +761,40 @@ int leaves_stage(grace_b200_ctx* ctx, size_t n, const T* d_deltas, int mpl, int4
     return GRACE_B200_OK;
 }
 
-// Stage 2 (build_nodes): `cap` bounds the leaf count, which is read on the device (d_nleaves).
+// Stage 2 (build_nodes): `cap` bounds the leaf count, which is read on the device (d_nleaves).  `boxes` is scratch for
+// two float4 per leaf.
 template <typename T>
 int nodes_stage(grace_b200_ctx* ctx, const float4* d_prims, bool from_aabb, size_t cap, const int4* d_leaves,
-                const int* d_nleaves, const T* leaf_deltas, unsigned* flags, int4* d_nodes, int* d_root, cudaStream_t st)
+                const int* d_nleaves, const T* leaf_deltas, unsigned* flags, float4* boxes, int4* d_nodes, int* d_root,
+                cudaStream_t st)
 {
-    // warps take tickets for ND_GROUP-leaf groups; the grid is what the SMs can hold
+    // (1) leaf boxes: warps stride over rows of 32 leaves
+    {
+        const size_t smem = (size_t)(LB_THREADS / 32) * LB_SLAB * (from_aabb ? 2 : 1) * sizeof(float4);
+        auto launch = [&](auto kernel) -> int {
+            GB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int per_sm = 0;
+            GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, LB_THREADS, smem));
+            const int need = (int)std::min<size_t>((cap + LB_THREADS - 1) / LB_THREADS, 1u << 30);
+            const int blocks = std::max(1, std::min(need, ctx->sm_count * std::max(per_sm, 1)));
+            kernel<<<blocks, LB_THREADS, smem, st>>>(d_prims, d_leaves, d_nleaves, boxes);
+            return GRACE_B200_OK;
+        };
+        const int lrc = from_aabb ? launch(leaf_boxes_kernel<true>) : launch(leaf_boxes_kernel<false>);
+        if (lrc) return lrc;
+        GB_LAUNCH_CHECK();
+    }
+    // (2) nodes: warps take tickets for ND_GROUP-leaf groups; the grid is what the SMs can hold
     int* nd_ticket = ctx->d_scalars + GB_SC_TICKET2;
     GB_CUDA(cudaMemsetAsync(nd_ticket, 0, sizeof(int), st));
     const size_t smem = (size_t)ND_WARPS * ND_GROUP * sizeof(NdSub<T>);
-    auto launch = [&](auto kernel) -> int {
-        GB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 0;
-        GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, ND_THREADS, smem));
-        const int need = (int)std::min<size_t>((cap + (size_t)ND_WARPS * ND_GROUP - 1) / ((size_t)ND_WARPS * ND_GROUP), 1u << 30);
-        const int nd_blocks = std::max(1, std::min(need, ctx->sm_count * std::max(per_sm, 1)));
-        kernel<<<nd_blocks, ND_THREADS, smem, st>>>(d_prims, d_leaves, d_nleaves, leaf_deltas, d_nodes, flags, d_root, nd_ticket);
-        return GRACE_B200_OK;
-    };
-    int lrc = from_aabb ? launch(nodes_kernel<T, true>) : launch(nodes_kernel<T, false>);
-    if (lrc) return lrc;
+    auto kernel = nodes_kernel<T>;
+    GB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, ND_THREADS, smem));
+    const int need = (int)std::min<size_t>((cap + (size_t)ND_WARPS * ND_GROUP - 1) / ((size_t)ND_WARPS * ND_GROUP), 1u << 30);
+    const int nd_blocks = std::max(1, std::min(need, ctx->sm_count * std::max(per_sm, 1)));
+    kernel<<<nd_blocks, ND_THREADS, smem, st>>>(boxes, d_nleaves, leaf_deltas, d_nodes, flags, d_root, nd_ticket);
     GB_LAUNCH_CHECK();
     return GRACE_B200_OK;
 }
@@ -748,7 +809,7 @@ int build_typed(grace_b200_ctx* ctx, const float4* d_spheres, size_t n, const T*
     if ((rc = leaves_stage<T>(ctx, n, d_deltas, mpl, d_leaves, w, st))) return rc;
     // the leaf count is only known on the device (anything up to n)
     return nodes_stage<T>(ctx, d_spheres, from_aabb, n, d_leaves, ctx->d_scalars + GB_SC_NLEAVES, w.leaf_deltas, w.flags,
-                          d_nodes, d_root, st);
+                          w.leaf_boxes, d_nodes, d_root, st);
 }
 
 __global__ void set_int_kernel(int* p, int v) { *p = v; }
@@ -893,28 +954,30 @@ static int albvh_nodes_any(grace_b200_ctx* ctx, const float* d_prims, bool from_
           int rc = build_workspace<T>(ctx, n, &w);                                                         \
           if (rc) return rc;                                                                               \
           return nodes_stage<T>(ctx, (const float4*)d_prims, from_aabb, n_leaves, (const int4*)d_leaves, d_nl, w.leaf_deltas, \
-                                w.flags, (int4*)d_nodes, d_root, st); }
+                                w.flags, w.leaf_boxes, (int4*)d_nodes, d_root, st); }
         if (delta_type == GRACE_B200_DELTA_F32) GB_NODES_CASE(float)
         if (delta_type == GRACE_B200_DELTA_U32) GB_NODES_CASE(uint32_t)
         if (delta_type == GRACE_B200_DELTA_U64) GB_NODES_CASE(uint64_t)
 #undef GB_NODES_CASE
         return gb_set_error(GRACE_B200_EINVAL, "unknown delta_type %d", delta_type);
     }
-    unsigned* flags = (unsigned*)gb_workspace(ctx, gb_align(n_leaves * sizeof(unsigned)) + 256);
+    const size_t flag_bytes = gb_align(n_leaves * sizeof(unsigned));
+    unsigned* flags = (unsigned*)gb_workspace(ctx, flag_bytes + gb_align(2 * n_leaves * sizeof(float4)) + 256);
     if (!flags) return GRACE_B200_ENOMEM;
+    float4* boxes = (float4*)((char*)flags + flag_bytes);
     GB_CUDA(cudaMemsetAsync(flags, 0, n_leaves * sizeof(unsigned), st));
     int* d_nleaves = ctx->d_scalars + GB_SC_NLEAVES;
     set_int_kernel<<<1, 1, 0, st>>>(d_nleaves, (int)n_leaves);
     GB_LAUNCH_CHECK();
     if (delta_type == GRACE_B200_DELTA_F32)
         return nodes_stage<float>(ctx, (const float4*)d_prims, from_aabb, n_leaves, (const int4*)d_leaves, d_nleaves,
-                                  (const float*)d_leaf_deltas, flags, (int4*)d_nodes, d_root, st);
+                                  (const float*)d_leaf_deltas, flags, boxes, (int4*)d_nodes, d_root, st);
     if (delta_type == GRACE_B200_DELTA_U32)
         return nodes_stage<uint32_t>(ctx, (const float4*)d_prims, from_aabb, n_leaves, (const int4*)d_leaves, d_nleaves,
-                                     (const uint32_t*)d_leaf_deltas, flags, (int4*)d_nodes, d_root, st);
+                                     (const uint32_t*)d_leaf_deltas, flags, boxes, (int4*)d_nodes, d_root, st);
     if (delta_type == GRACE_B200_DELTA_U64)
         return nodes_stage<uint64_t>(ctx, (const float4*)d_prims, from_aabb, n_leaves, (const int4*)d_leaves, d_nleaves,
-                                     (const uint64_t*)d_leaf_deltas, flags, (int4*)d_nodes, d_root, st);
+                                     (const uint64_t*)d_leaf_deltas, flags, boxes, (int4*)d_nodes, d_root, st);
     return gb_set_error(GRACE_B200_EINVAL, "unknown delta_type %d", delta_type);
 }
 
