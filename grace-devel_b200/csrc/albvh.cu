@@ -10,22 +10,22 @@
 //   delta(l-1) < delta(r), else the LEFT child of node r (ties go right);
 //   leaves = maximal subtrees with <= max_per_leaf primitives.
 //
-// B200 design -- two launches, no host round trip, no Thrust:
-//  (1) leaves_kernel: node j's subtree is [l_j, r_j] with l_j = 1 + (last k < j with
-//      delta_k >= delta_j) and r_j = (first k > j with delta_k > delta_j): the
-//      Cartesian tree of the deltas under the tie rule above.  Each thread bounds its
-//      two scans at max_per_leaf+1 steps over a shared-memory window of deltas, so
-//      "is my left/right child a leaf" needs no atomics and no temporary node array.
-//      Emitted leaves (0..2 per node, ordered by node index == ordered by primitive
-//      range) are compacted in the same kernel with a decoupled look-back scan; the
-//      leaf-level deltas and the zeroed arrival flags are written alongside.
-//  (2) nodes_kernel: classic Karras/Apetrei bottom-up climb over the L leaves with one
-//      global arrival counter per node.  8 lanes cooperate on a leaf's AABB (coalesced
-//      128 B segments of the sphere array), then the group leader climbs, writing its
-//      child index / range end / AABB into the parent's 64-byte record (the reference
-//      layout, cuda/nodes.h:21-36) and continuing only as the second arrival.
-// Algorithmic bytes per particle: deltas 16+4; leaves 4 + (16+4+4)*L/N;
-// nodes 16 + (16 + 2*64)*L/N.
+// B200 design -- three launches, no host round trip, no Thrust:
+//  (1) leaves: node j's subtree is [l_j, r_j] with l_j = 1 + (last k < j with delta_k >= delta_j) and
+//      r_j = (first k > j with delta_k > delta_j): the Cartesian tree of the deltas under the tie rule
+//      above.  Leaves are the stretches between consecutive nodes whose subtree exceeds max_per_leaf;
+//      for max_per_leaf = 32 those nodes are found as sliding-window maxima (leaves_window_kernel),
+//      otherwise from bounded scans over a shared-memory table (leaves_kernel).  No atomics, no
+//      temporary node array; the leaves (ordered by primitive range) are compacted in the same kernel
+//      with a decoupled look-back scan, the leaf-level deltas and the zeroed arrival flags are written
+//      alongside.
+//  (2) leaf_boxes_kernel: one AABB per leaf, spheres staged through shared memory with coalesced loads.
+//  (3) nodes_kernel: subtrees merged in registers and shared memory per warp (no atomics for ~90 % of
+//      the nodes), then a Karras/Apetrei bottom-up climb with one global arrival counter per node for
+//      what is left, writing child index / range end / AABB into the parent's 64-byte record (the
+//      reference layout, cuda/nodes.h:21-36).
+// Algorithmic bytes per particle: deltas 16+4; leaves 4 + (16+4+4)*L/N; leaf boxes 16 + 32*L/N;
+// nodes (32 + 2*64)*L/N.
 #include "common.cuh"
 
 #include <math_constants.h>
