@@ -360,12 +360,14 @@ def run_b200(args):
         result_sha1 = hashlib.sha1(final.cpu().numpy().tobytes()).hexdigest()[:16]
         del single
 
-    # ---- e2e: from HOST buffers -- particles H2D, broadcast, tree build, rays H2D (+ broadcast), trace,
+    # ---- e2e: from HOST buffers -- particles H2D, broadcast, tree build, rays H2D (each rank its share), trace,
     #      gather, result D2H -- every step ----
     e2e_steps = max(1, min(args.steps, 10))
-    h_rays = rays.cpu().pin_memory() if rank == 0 else None
+    # every rank holds its share of the rays in pinned host memory and copies it over its own PCIe link (rank 0
+    # copying all rays and broadcasting them was 4 ms of every step at any N)
+    h_rays_local = gb.take_local(rays, rank, world, TILE).cpu().pin_memory()
     h_out = torch.empty(r, dtype=torch.float32).pin_memory() if rank == 0 else None
-    d_rays2 = torch.empty_like(rays)
+    d_rays_local = torch.empty((h_rays_local.shape[0], 7), dtype=torch.float32, device=dev)
     e2e_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(e2e_steps)]
     saved_tree = tree
     for k in range(1 + e2e_steps):
@@ -378,11 +380,8 @@ def run_b200(args):
         if world > 1:
             dist.broadcast(spheres, src=0)
         tree = build(spheres)
-        if rank == 0:
-            d_rays2.copy_(h_rays, non_blocking=True)
-        if world > 1:
-            dist.broadcast(d_rays2, src=0)
-        step(gb.take_local(d_rays2, rank, world, TILE))
+        d_rays_local.copy_(h_rays_local, non_blocking=True)
+        step(d_rays_local)
         if rank == 0:
             h_out.copy_(result[0], non_blocking=True)
         if k >= 1:
@@ -563,7 +562,7 @@ def run_b200(args):
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": "Mrays/s", "ms_per_step": e2e_ms, "steps": e2e_steps,
                 "h2d_bytes_per_step": int(n * 16 + r * 28), "d2h_bytes_per_step": int(r * 4),
-                "what": "particles H2D + NCCL broadcast + tree build on every rank + rays H2D (+ broadcast) + trace + "
+                "what": "particles H2D + NCCL broadcast + tree build on every rank + H2D of each rank's share of the rays + trace + "
                         "all-gather + reassembly + result D2H, every step"},
         # trace_cumulative_sph = 2 launches of trace_packet_kernel (packets with work stealing, fold) per rank
         "gpu_launches": args.steps * world * 2,
@@ -618,9 +617,19 @@ def run_config5(args, gb, dist, world, rank, dev, barrier, max_over_ranks):
         # nodes 0.43 GB + leaves 0.1 GB over NVLink): with every rank building its own copy the build was the
         # Amdahl term of this configuration -- and ran 2x slower per rank than alone.
         tree5 = gb.Tree(2, args.max_per_leaf) if rank else gb.Tree(n5, args.max_per_leaf)
+        # build_tree (tests/helper/tree.cuh:15-43) in its three steps: the sorted particles are final after the first, so
+        # their broadcast (2 GiB, the bulk of the tree) runs on NCCL's stream while rank 0 computes deltas, leaves and nodes
+        sent = None
         if rank == 0:
             s5.copy_(src)
-            gb.build_tree(s5, tree5, key_bits=63)
+            gb.morton_keys63_sort_sph(s5)
+        if world > 1:
+            sent = dist.broadcast(s5, src=0, async_op=True)
+        if rank == 0:
+            deltas5 = torch.empty(n5 + 1, dtype=torch.float32, device=dev)
+            gb.euclidean_deltas_sph(s5, deltas5)
+            gb.ALBVH_sph(s5, deltas5, tree5)
+            del deltas5
         e[1].record(stream)
         if world > 1:
             nl = torch.tensor([tree5.n_leaves if rank == 0 else 0], dtype=torch.int64, device=dev)
@@ -629,8 +638,9 @@ def run_config5(args, gb, dist, world, rank, dev, barrier, max_over_ranks):
             if rank:
                 tree5.nodes = torch.empty((L - 1, 16), dtype=torch.int32, device=dev)
                 tree5.leaves = torch.empty((L, 4), dtype=torch.int32, device=dev)
-            for t in (s5, tree5.nodes, tree5.leaves, tree5.root_index_ptr):
+            for t in (tree5.nodes, tree5.leaves, tree5.root_index_ptr):
                 dist.broadcast(t, src=0)
+            sent.wait()
         e[2].record(stream)
         gb.trace_cumulative_sph(local5, s5, tree5, out5)
         if world > 1:
@@ -654,8 +664,8 @@ def run_config5(args, gb, dist, world, rank, dev, barrier, max_over_ranks):
     return {"workload": "one_to_many_rays (A): 2^27 particles, 63-bit keys, 2^24 HEALPix NESTED rays (nside 2048, pixels [0, 2^24))",
             "n_gpus": world, "build_and_tree_broadcast_ms": statistics.mean(t_b), "trace_gather_ms": tt,
             "end_to_end_ms": ta, "mrays_s_trace_gather": r5 / tt / 1e3, "mrays_s_end_to_end": r5 / ta / 1e3,
-            "end_to_end": "tree build on rank 0 + NCCL broadcast of the finished tree (sorted particles, nodes, leaves, root) + "
-                          "trace of the rank's tiles + all-gather + reassembly",
+            "end_to_end": "tree build on rank 0 + NCCL broadcast of the finished tree (sorted particles -- sent while deltas, leaves and "
+                          "nodes are computed --, nodes, leaves, root) + trace of the rank's tiles + all-gather + reassembly",
             "n_leaves": n_leaves, "result_sha1_16": sha}
 
 
