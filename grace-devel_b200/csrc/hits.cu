@@ -164,8 +164,11 @@ classify_kernel(const int* __restrict__ offsets, int n_rays, long long total,
 // 3 barriers per pass where the bitonic network it replaces needed one per compare-exchange stage
 // (66 for 2048 elements, 91 for 8192).  A pass whose digit is the same for the whole segment is
 // skipped.  The permutation is then applied to distances, indices and payload in place.
+// (capped at 56 registers: the kernel is a chain of barrier-separated phases and more resident CTAs hide them;
+// 96-128 registers -> 5.31 ms, 80 -> 4.78, 64 -> 4.75, 56 -> 4.61, 48 -> 4.62 for the 1.68e8 hits of 2^17 rays)
+constexpr int SS_REGS = 56;
 template <int CAP, int NT>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 65536 / (NT * SS_REGS) > 16 ? 16 : 65536 / (NT * SS_REGS))
 segsort_smem_kernel(float* __restrict__ dist, const int* __restrict__ offsets, int n_rays,
                     long long total, int* __restrict__ idx, unsigned* __restrict__ data,
                     const int* __restrict__ list, const int* __restrict__ count_ptr)
